@@ -1,0 +1,130 @@
+/*
+ * smaat_b200.h -- C ABI of libsmaat_b200.so: the B200 (sm_100a) kernels behind the
+ * SmaAt-UNet forward hot path (depthwise-separable conv blocks + CBAM + their glue).
+ *
+ * The reference (HansBambel/SmaAt-UNet) has no FFI / plugin registry: its boundary is
+ * the Python nn.Module interface.  Each entry point below
+ * replaces the torch.nn call(s) cited next to it; `smaat_unet_b200/modules.py` is the
+ * host-side mirror of the reference classes that binds them through ctypes, and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - all tensors are fp32, NCHW, dense in (H, W); device pointers owned by the caller
+ *     (PyTorch caching allocator).  The library allocates nothing persistent.
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*):
+ *     no device synchronisation, no allocation -> CUDA-graph capturable.
+ *   - return value: 0 on success, negative SMAAT_E_* otherwise; smaat_last_error()
+ *     returns a thread-local description.  Nothing throws or exits across the ABI.
+ *   - "bstride" arguments are batch strides in ELEMENTS (>= C*H*W) so a kernel can
+ *     read from / write into a channel slice of a wider tensor without a copy.
+ */
+#ifndef SMAAT_B200_H_
+#define SMAAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMAAT_ABI_VERSION 1
+
+#define SMAAT_OK 0
+#define SMAAT_E_BADARG (-1)   /* shape / pointer / alignment rejected by host-side validation */
+#define SMAAT_E_CUDA (-2)     /* CUDA runtime or driver error at launch (see smaat_last_error) */
+#define SMAAT_E_UNSUPPORTED (-3) /* valid request this build has no kernel for */
+
+/* pointwise arithmetic modes (smaat_pw1x1_fwd) */
+#define SMAAT_PW_FP32_SIMT 0  /* CUDA-core FFMA, exact fp32 products                      */
+#define SMAAT_PW_TF32 1       /* tcgen05 kind::tf32, fp32 accumulate in TMEM (1 pass)     */
+#define SMAAT_PW_TF32X3 2     /* tcgen05 3xTF32 split (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo) */
+
+int smaat_abi_version(void);
+const char* smaat_last_error(void);
+/* Number of kernel launches enqueued by this library in the calling process so far. */
+uint64_t smaat_launch_count(void);
+
+/* ---- depthwise 3x3, padding 1, groups=Cin, k outputs per input channel -------------
+ * replaces DepthwiseSeparableConv.depthwise  (models/layers.py:38-44,48)
+ * Input is the virtual channel-concat of x0 (C0 channels) and x1 (C1 channels, may be
+ * NULL/0): this is torch.cat([x2, x1], dim=1) of UpDS.forward
+ * (models/unet_parts_depthwise_separable.py:85) without materialising the concat.
+ * y[b, o] = bias[o] + sum_{dy,dx} w[o,dy,dx] * in[b, o / k, i+dy-1, j+dx-1]
+ *   w: (k*(C0+C1), 3, 3)   bias: (k*(C0+C1)) or NULL   y: (B, k*(C0+C1), H, W) dense
+ * in_scale/in_shift (per INPUT channel, may be NULL): when given the kernel applies
+ *   relu(in_scale[c] * x + in_shift[c]) on load -- the train-mode BatchNorm+ReLU of the
+ *   producing layer (parts_ds.py:25-26), with zero padding applied AFTER the activation.
+ * loader: 0 = auto, 1 = force the LDG loader, 2 = force TMA (error if ineligible). */
+int smaat_dw3x3_fwd(const float* x0, int C0, int64_t x0_bstride,
+                    const float* x1, int C1, int64_t x1_bstride,
+                    const float* w, const float* bias,
+                    const float* in_scale, const float* in_shift,
+                    float* y, int B, int H, int W, int k, int loader, void* stream);
+
+/* ---- pointwise 1x1 + per-channel affine (+ReLU) epilogue -----------------------------
+ * replaces DepthwiseSeparableConv.pointwise (models/layers.py:45,49) fused with the
+ * following nn.BatchNorm2d (eval) + nn.ReLU (parts_ds.py:25-26,34-35):
+ *   y[b,o,p] = act( scale[o] * sum_c w[o,c] x[b,c,p] + shift[o] )
+ *   x: (B, K, P) dense   w: (Cout, K)   scale/shift: (Cout) (scale NULL = 1, shift NULL = 0)
+ *   y: (B, Cout, P) with batch stride y_bstride elements.
+ * w_lo: (Cout, K) low parts for SMAAT_PW_TF32X3 (w must then hold the tf32-truncated
+ *   high parts, see smaat_split_tf32); NULL otherwise.
+ * stats: NULL, or (2*Cout) fp32 zero-initialised accumulators receiving per-channel
+ *   sum and sum of squares of the PRE-activation value scale*acc+shift (train-mode BN). */
+int smaat_pw1x1_fwd(const float* x, const float* w, const float* w_lo,
+                    const float* scale, const float* shift,
+                    float* y, int64_t y_bstride, float* stats,
+                    int B, int K, int Cout, int P, int relu, int mode, void* stream);
+
+/* 1 if this (x, w, K, Cout, P) can take the tcgen05 path (P % 4 == 0, K % 4 == 0, 16-byte aligned
+ * pointers, Cout >= 8), else 0: the caller then uses SMAAT_PW_FP32_SIMT. */
+int smaat_pw1x1_tc_eligible(const float* x, const float* w, int K, int Cout, int P);
+
+/* hi[i] = tf32_truncate(src[i]); lo[i] = src[i] - hi[i]   (weight preparation for TF32X3) */
+int smaat_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream);
+
+/* ---- eval-mode BatchNorm folded to the affine the pw epilogue applies -----------------
+ * nn.BatchNorm2d.eval (parts_ds.py:25,34):  scale = gamma / sqrt(rv + eps),
+ *   shift = beta + (conv_bias - rm) * scale        (conv_bias may be NULL) */
+int smaat_bn_fold(const float* gamma, const float* beta, const float* rm, const float* rv,
+                  const float* conv_bias, float eps, float* scale, float* shift, int C, void* stream);
+
+/* ---- nn.MaxPool2d(2) (parts_ds.py:48): stride 2, floor ---------------------------------
+ * x: (N, H, W) planes -> y: (N, H/2, W/2) */
+int smaat_maxpool2_fwd(const float* x, float* y, int64_t N, int H, int W, void* stream);
+
+/* ---- nn.Upsample(x2, bilinear, align_corners=True) + F.pad to the skip size -----------
+ * (parts_ds.py:64,78-81).  x: (B, C, H, W) -> y: (B, C, Ho, Wo) with Ho >= 2H, Wo >= 2W,
+ * zero border of (Ho-2H)//2 rows on top, (Wo-2W)//2 columns on the left. */
+int smaat_upsample2x_pad_fwd(const float* x, float* y, int64_t y_bstride,
+                             int B, int C, int H, int W, int Ho, int Wo, void* stream);
+
+/* ---- CBAM (models/layers.py:90-141) -----------------------------------------------------
+ * pool:   avg[n] = mean_p x[n,p], mx[n] = max_p x[n,p] over N = B*C planes of P pixels
+ *         (AdaptiveAvgPool2d(1)/AdaptiveMaxPool2d(1), layers.py:107-108)
+ * mlp:    sc[b,c] = sigmoid( MLP(avg[b]) + MLP(mx[b]) ), MLP = W2 relu(W1 v + b1) + b2
+ *         (layers.py:98-103,109)
+ * reduce: pooled[b,0,p] = mean_c x[b,c,p]*sc[b,c]; pooled[b,1,p] = max_c ...  (layers.py:123-125)
+ * gate:   a = conv_kxk(pooled, wsp)  (2->1 ch, pad k/2, no bias, layers.py:119,126);
+ *         sa[b,p] = sigmoid(bn_affine[0] * a + bn_affine[1])  (BatchNorm2d(1) + sigmoid, :127-128);
+ *         bn_affine = 2 floats ON THE DEVICE (smaat_bn_fold with C=1), NULL = identity;
+ *         if raw != NULL the pre-BN conv output a is also written (train-mode statistics).
+ * scale:  y[b,c,p] = x[b,c,p] * sc[b,c] * sa[b,p]   (layers.py:110,128) */
+int smaat_cbam_pool_fwd(const float* x, float* avg, float* mx, int64_t N, int P, void* stream);
+int smaat_cbam_mlp_fwd(const float* avg, const float* mx, const float* w1, const float* b1,
+                       const float* w2, const float* b2, float* sc, int B, int C, int hidden, void* stream);
+int smaat_cbam_reduce_fwd(const float* x, const float* sc, float* pooled, int B, int C, int P, void* stream);
+int smaat_cbam_gate_fwd(const float* pooled, const float* wsp, const float* bn_affine, float* sa, float* raw,
+                        int B, int H, int W, int ks, void* stream);
+int smaat_cbam_scale_fwd(const float* x, const float* sc, const float* sa, float* y, int64_t y_bstride,
+                         int B, int C, int P, void* stream);
+
+/* ---- OutConv (models/unet_parts.py:67-73): 1x1 conv Cin -> ncls (small), bias, no activation */
+int smaat_outconv_fwd(const float* x, const float* w, const float* bias, float* y,
+                      int B, int Cin, int ncls, int P, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMAAT_B200_H_ */

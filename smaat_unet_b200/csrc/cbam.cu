@@ -1,0 +1,344 @@
+// cbam.cu -- CBAM channel + spatial attention, forward (reference models/layers.py:90-141).
+//
+// Op-level traffic: the HW-global pool forces two reads of x before anything can be scaled,
+// so the practical minimum is pool (1R) + channel-reduce (1R) + scale (1R+1W) = 4 |x|
+// (SURVEY 8d).  Kernels:
+//   pool    per-(b,c) plane mean+max           -- 128-bit loads, warp-shuffle + smem tree
+//   mlp     shared 2-layer MLP + sigmoid       -- tiny, one CTA per image
+//   reduce  per-pixel mean/max over channels of x*sc -> [B,2,H,W]
+//   gate    k x k conv (2->1) + BN(1) affine + sigmoid on the small map
+//   scale   y = (x*sc)*sa                      -- 128-bit streaming
+#include "common.cuh"
+
+namespace smaat {
+
+__device__ __forceinline__ float sigmoidf_acc(float v) { return 1.f / (1.f + expf(-v)); }
+
+// ---- pool ----------------------------------------------------------------------------------------
+// TPP threads cooperate on one plane; blockDim.x / TPP planes per CTA.
+template <int TPP, bool VEC>
+__global__ void __launch_bounds__(256) cbam_pool_kernel(const float* __restrict__ x, float* __restrict__ avg,
+                                                        float* __restrict__ mx, int64_t N, int P) {
+  constexpr int PPB = 256 / TPP;
+  const int sub = threadIdx.x / TPP;
+  const int lane = threadIdx.x % TPP;
+  const int64_t n = (int64_t)blockIdx.x * PPB + sub;
+  float s = 0.f, m = -INFINITY;
+  if (n < N) {
+    const float* src = x + n * (int64_t)P;
+    if (VEC) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      const int n4 = P >> 2;
+      int i = lane;
+      // 4 independent 128-bit loads in flight per thread
+      for (; i + 3 * TPP < n4; i += 4 * TPP) {
+        const float4 a = __ldg(s4 + i), b = __ldg(s4 + i + TPP), c = __ldg(s4 + i + 2 * TPP), d = __ldg(s4 + i + 3 * TPP);
+        s += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) + ((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w));
+        m = fmaxf(m, fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+        m = fmaxf(m, fmaxf(fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, c.w)), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w))));
+      }
+      for (; i < n4; i += TPP) {
+        const float4 a = __ldg(s4 + i);
+        s += (a.x + a.y) + (a.z + a.w);
+        m = fmaxf(m, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+      }
+    } else {
+      for (int i = lane; i < P; i += TPP) {
+        const float v = __ldg(src + i);
+        s += v;
+        m = fmaxf(m, v);
+      }
+    }
+  }
+  s = warp_sum(s);
+  m = warp_max(m);
+  if (TPP == 32) {
+    if (lane == 0 && n < N) {
+      avg[n] = s / (float)P;
+      mx[n] = m;
+    }
+  } else {
+    __shared__ float ss[8], sm[8];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+      ss[w] = s;
+      sm[w] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && n < N) {
+      float S = 0.f, M = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        S += ss[i];
+        M = fmaxf(M, sm[i]);
+      }
+      avg[n] = S / (float)P;
+      mx[n] = M;
+    }
+  }
+}
+
+// ---- shared MLP + sigmoid ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cbam_mlp_kernel(const float* __restrict__ avg, const float* __restrict__ mx,
+                                                       const float* __restrict__ w1, const float* __restrict__ b1,
+                                                       const float* __restrict__ w2, const float* __restrict__ b2,
+                                                       float* __restrict__ sc, int C, int hidden) {
+  extern __shared__ float sh[];  // avg[C] mx[C] ha[hidden] hm[hidden]
+  float* sa = sh;
+  float* sm = sh + C;
+  float* ha = sm + C;
+  float* hm = ha + hidden;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sa[c] = avg[(int64_t)b * C + c];
+    sm[c] = mx[(int64_t)b * C + c];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < hidden; j += nw) {
+    float da = 0.f, dm = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float wv = __ldg(w1 + (int64_t)j * C + c);
+      da = fmaf(wv, sa[c], da);
+      dm = fmaf(wv, sm[c], dm);
+    }
+    da = warp_sum(da);
+    dm = warp_sum(dm);
+    if (lane == 0) {
+      ha[j] = fmaxf(da + b1[j], 0.f);
+      hm[j] = fmaxf(dm + b1[j], 0.f);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float oa = b2[c], om = b2[c];  // second-layer bias is counted twice (layers.py:109)
+    for (int j = 0; j < hidden; ++j) {
+      const float wv = __ldg(w2 + (int64_t)c * hidden + j);
+      oa = fmaf(wv, ha[j], oa);
+      om = fmaf(wv, hm[j], om);
+    }
+    sc[(int64_t)b * C + c] = sigmoidf_acc(oa + om);
+  }
+}
+
+// ---- per-pixel channel mean / max of x*sc --------------------------------------------------------------
+// blockDim = (32 pixel-quads, 8 channel groups); smem tree over the 8 groups.
+template <bool VEC>
+__global__ void __launch_bounds__(256) cbam_reduce_kernel(const float* __restrict__ x, const float* __restrict__ sc,
+                                                          float* __restrict__ pooled, int C, int P) {
+  __shared__ float4 rs[8][32];
+  __shared__ float4 rm[8][32];
+  const int tx = threadIdx.x, cg = threadIdx.y;
+  const int b = blockIdx.y;
+  const int pp = (blockIdx.x * 32 + tx) * 4;
+  const float* xb = x + (int64_t)b * C * P;
+  const float* scb = sc + (int64_t)b * C;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  if (pp < P) {
+#pragma unroll 4
+    for (int c = cg; c < C; c += 8) {
+      const float g = __ldg(scb + c);
+      float4 v;
+      const float* src = xb + (int64_t)c * P + pp;
+      if (VEC) {
+        v = __ldg(reinterpret_cast<const float4*>(src));
+      } else {
+        v.x = __ldg(src);
+        v.y = (pp + 1 < P) ? __ldg(src + 1) : 0.f;
+        v.z = (pp + 2 < P) ? __ldg(src + 2) : 0.f;
+        v.w = (pp + 3 < P) ? __ldg(src + 3) : 0.f;
+      }
+      v.x *= g; v.y *= g; v.z *= g; v.w *= g;
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  }
+  rs[cg][tx] = s;
+  rm[cg][tx] = m;
+  __syncthreads();
+  if (cg == 0 && pp < P) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const float4 a = rs[i][tx], q = rm[i][tx];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      m.x = fmaxf(m.x, q.x); m.y = fmaxf(m.y, q.y); m.z = fmaxf(m.z, q.z); m.w = fmaxf(m.w, q.w);
+    }
+    const float inv = 1.f / (float)C;
+    float* pa = pooled + (int64_t)b * 2 * P + pp;
+    float* pm = pa + P;
+    const float4 mean = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+    if (VEC) {
+      *reinterpret_cast<float4*>(pa) = mean;
+      *reinterpret_cast<float4*>(pm) = m;
+    } else {
+      const float me[4] = {mean.x, mean.y, mean.z, mean.w};
+      const float ma[4] = {m.x, m.y, m.z, m.w};
+      for (int q = 0; q < 4; ++q)
+        if (pp + q < P) {
+          pa[q] = me[q];
+          pm[q] = ma[q];
+        }
+    }
+  }
+}
+
+// ---- spatial gate: conv kxk (2->1) + affine + sigmoid ------------------------------------------------
+constexpr int GT_W = 32, GT_H = 16;
+template <int KS>
+__global__ void __launch_bounds__(256) cbam_gate_kernel(const float* __restrict__ pooled, const float* __restrict__ wsp,
+                                                        const float* __restrict__ bn_affine, float* __restrict__ sa,
+                                                        float* __restrict__ raw, int H, int W) {
+  constexpr int R = KS / 2;
+  constexpr int SW = GT_W + 2 * R, SH = GT_H + 2 * R;
+  __shared__ float t[2][SH][SW + 1];
+  __shared__ float wk[2 * KS * KS];
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H;
+  const int tid = threadIdx.x;
+  if (tid < 2 * KS * KS) wk[tid] = __ldg(wsp + tid);
+  const float* pb = pooled + (int64_t)b * 2 * H * W;
+  for (int i = tid; i < 2 * SH * SW; i += 256) {
+    const int ch = i / (SH * SW);
+    const int r = (i / SW) % SH, c = i % SW;
+    const int gy = y0 - R + r, gx = x0 - R + c;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(pb + ((int64_t)ch * H + gy) * W + gx);
+    t[ch][r][c] = v;
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;  // 32 x 8, two rows per thread
+  const float a_s = bn_affine ? __ldg(bn_affine) : 1.f;
+  const float a_t = bn_affine ? __ldg(bn_affine + 1) : 0.f;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int oy = ty + half * 8;
+    const int gy = y0 + oy, gx = x0 + tx;
+    float acc = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+      for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < KS; ++dx) acc = fmaf(wk[(ch * KS + dy) * KS + dx], t[ch][oy + dy][tx + dx], acc);
+    if (gy < H && gx < W) {
+      const int64_t o = ((int64_t)b * H + gy) * W + gx;
+      if (raw) raw[o] = acc;
+      sa[o] = sigmoidf_acc(fmaf(acc, a_s, a_t));
+    }
+  }
+}
+
+// ---- y = (x * sc) * sa -------------------------------------------------------------------------------------
+constexpr int SC_CH = 8;  // channels per thread (sa quad reused from registers)
+template <bool VEC>
+__global__ void __launch_bounds__(256) cbam_scale_kernel(const float* __restrict__ x, const float* __restrict__ sc,
+                                                         const float* __restrict__ sa, float* __restrict__ y,
+                                                         int64_t y_bstride, int C, int P) {
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * SC_CH;
+  const int pp = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (pp >= P) return;
+  float4 g;
+  const float* sab = sa + (int64_t)b * P + pp;
+  if (VEC) {
+    g = __ldg(reinterpret_cast<const float4*>(sab));
+  } else {
+    g.x = __ldg(sab);
+    g.y = (pp + 1 < P) ? __ldg(sab + 1) : 0.f;
+    g.z = (pp + 2 < P) ? __ldg(sab + 2) : 0.f;
+    g.w = (pp + 3 < P) ? __ldg(sab + 3) : 0.f;
+  }
+  const float* xb = x + ((int64_t)b * C + c0) * P + pp;
+  float* yb = y + (int64_t)b * y_bstride + (int64_t)c0 * P + pp;
+  const float* scb = sc + (int64_t)b * C + c0;
+  const int nc = min(SC_CH, C - c0);
+  if (VEC && nc == SC_CH) {
+    float4 v[SC_CH];
+#pragma unroll
+    for (int i = 0; i < SC_CH; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)i * P));
+#pragma unroll
+    for (int i = 0; i < SC_CH; ++i) {
+      const float s = __ldg(scb + i);
+      float4 o;
+      o.x = (v[i].x * s) * g.x; o.y = (v[i].y * s) * g.y; o.z = (v[i].z * s) * g.z; o.w = (v[i].w * s) * g.w;
+      *reinterpret_cast<float4*>(yb + (int64_t)i * P) = o;
+    }
+  } else {
+    const float gg[4] = {g.x, g.y, g.z, g.w};
+    for (int i = 0; i < nc; ++i) {
+      const float s = __ldg(scb + i);
+      for (int q = 0; q < 4; ++q)
+        if (pp + q < P) yb[(int64_t)i * P + q] = (__ldg(xb + (int64_t)i * P + q) * s) * gg[q];
+    }
+  }
+}
+
+}  // namespace smaat
+
+using namespace smaat;
+
+extern "C" int smaat_cbam_pool_fwd(const float* x, float* avg, float* mx, int64_t N, int P, void* stream) {
+  SMAAT_REQUIRE(x && avg && mx && N > 0 && P > 0, "cbam_pool: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (P % 4 == 0) && aligned16(x);
+  if (P >= 2048) {
+    SMAAT_REQUIRE(N < (1ll << 31), "cbam_pool: too many planes");
+    if (vec) cbam_pool_kernel<256, true><<<(unsigned)N, 256, 0, st>>>(x, avg, mx, N, P);
+    else cbam_pool_kernel<256, false><<<(unsigned)N, 256, 0, st>>>(x, avg, mx, N, P);
+  } else {
+    const unsigned grid = (unsigned)ceil_div64(N, 8);
+    if (vec) cbam_pool_kernel<32, true><<<grid, 256, 0, st>>>(x, avg, mx, N, P);
+    else cbam_pool_kernel<32, false><<<grid, 256, 0, st>>>(x, avg, mx, N, P);
+  }
+  SMAAT_LAUNCH_CHECK("smaat_cbam_pool_fwd");
+  return SMAAT_OK;
+}
+
+extern "C" int smaat_cbam_mlp_fwd(const float* avg, const float* mx, const float* w1, const float* b1, const float* w2,
+                                  const float* b2, float* sc, int B, int C, int hidden, void* stream) {
+  SMAAT_REQUIRE(avg && mx && w1 && b1 && w2 && b2 && sc && B > 0 && C > 0 && hidden > 0, "cbam_mlp: bad arguments (hidden=%d)",
+                hidden);
+  const size_t smem = (size_t)(2 * C + 2 * hidden) * sizeof(float);
+  SMAAT_REQUIRE(smem <= 48 * 1024, "cbam_mlp: C=%d too large", C);
+  cbam_mlp_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(avg, mx, w1, b1, w2, b2, sc, C, hidden);
+  SMAAT_LAUNCH_CHECK("smaat_cbam_mlp_fwd");
+  return SMAAT_OK;
+}
+
+extern "C" int smaat_cbam_reduce_fwd(const float* x, const float* sc, float* pooled, int B, int C, int P, void* stream) {
+  SMAAT_REQUIRE(x && sc && pooled && B > 0 && C > 0 && P > 0, "cbam_reduce: bad arguments");
+  SMAAT_REQUIRE(B <= 65535, "cbam_reduce: batch too large for grid.y");
+  const bool vec = (P % 4 == 0) && aligned16(x) && aligned16(pooled);
+  dim3 grid(ceil_div(P, 128), B), block(32, 8);
+  if (vec) cbam_reduce_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(x, sc, pooled, C, P);
+  else cbam_reduce_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(x, sc, pooled, C, P);
+  SMAAT_LAUNCH_CHECK("smaat_cbam_reduce_fwd");
+  return SMAAT_OK;
+}
+
+extern "C" int smaat_cbam_gate_fwd(const float* pooled, const float* wsp, const float* bn_affine, float* sa, float* raw, int B,
+                                   int H, int W, int ks, void* stream) {
+  SMAAT_REQUIRE(pooled && wsp && sa && B > 0 && H > 0 && W > 0, "cbam_gate: bad arguments");
+  SMAAT_REQUIRE(ks == 3 || ks == 7, "cbam_gate: kernel size must be 3 or 7 (layers.py:117), got %d", ks);
+  SMAAT_REQUIRE(B <= 65535, "cbam_gate: batch too large for grid.z");
+  dim3 grid(ceil_div(W, GT_W), ceil_div(H, GT_H), B);
+  if (ks == 7) cbam_gate_kernel<7><<<grid, 256, 0, (cudaStream_t)stream>>>(pooled, wsp, bn_affine, sa, raw, H, W);
+  else cbam_gate_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(pooled, wsp, bn_affine, sa, raw, H, W);
+  SMAAT_LAUNCH_CHECK("smaat_cbam_gate_fwd");
+  return SMAAT_OK;
+}
+
+extern "C" int smaat_cbam_scale_fwd(const float* x, const float* sc, const float* sa, float* y, int64_t y_bstride, int B, int C,
+                                    int P, void* stream) {
+  SMAAT_REQUIRE(x && sc && sa && y && B > 0 && C > 0 && P > 0, "cbam_scale: bad arguments");
+  SMAAT_REQUIRE(y_bstride >= (int64_t)C * P, "cbam_scale: y batch stride too small");
+  SMAAT_REQUIRE(B <= 65535 && ceil_div(C, SC_CH) <= 65535, "cbam_scale: grid too large");
+  const bool vec = (P % 4 == 0) && aligned16(x) && aligned16(y) && aligned16(sa) && (y_bstride % 4 == 0);
+  const int threads = 128;
+  dim3 grid(ceil_div(ceil_div(P, 4), threads), ceil_div(C, SC_CH), B);
+  if (vec) cbam_scale_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(x, sc, sa, y, y_bstride, C, P);
+  else cbam_scale_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(x, sc, sa, y, y_bstride, C, P);
+  SMAAT_LAUNCH_CHECK("smaat_cbam_scale_fwd");
+  return SMAAT_OK;
+}

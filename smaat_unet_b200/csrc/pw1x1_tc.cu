@@ -1,0 +1,318 @@
+// pw1x1_tc.cu -- pointwise 1x1 conv on the 5th-gen tensor cores (tcgen05, TMEM accumulators),
+// fused with the per-channel affine (+ReLU) epilogue and optional BatchNorm statistics.
+//
+// Replaces DepthwiseSeparableConv.pointwise + eval BatchNorm2d + ReLU
+// (reference models/layers.py:45,49; parts_ds.py:25-26,34-35): the only dense contraction
+// on the SmaAt-UNet forward path.
+//
+// Mapping (per image b):  D[128 pixels x N_TILE channels] += A[128 px x 8] * B[N_TILE x 8]^T
+//   A = activations X[b] ([K][P], pixels contiguous)  -> "MN-major" smem operand: the NCHW
+//       tensor is consumed as it lies in HBM, no transpose, TMA boxes of 32 k-rows x 32 px
+//       with 128B swizzle (4 boxes = 128 pixels);
+//   B = weights W ([Cout][K], K contiguous)           -> K-major operand, one TMA box
+//       of N_TILE rows x 32 k with 128B swizzle;
+//   D in TMEM: lane = pixel, column = output channel, so tcgen05.ld.32x32b hands every warp
+//       32 consecutive pixels of one channel per register -> fully coalesced NCHW stores with
+//       no smem staging.  kind::tf32, fp32 accumulate.
+// TF32X3 mode (fp32-grade accuracy): activations are split in smem into a tf32 "hi" part and
+// the "lo" remainder by the 4 transform/epilogue warps; weights arrive pre-split; three MMAs
+// (hi*hi + lo*hi + hi*lo) per k-step accumulate into the same TMEM tile.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one
+// elected lane), warps 2-5 = [X3: hi/lo transform] + epilogue (warp w owns TMEM lanes
+// 32*(w%4) .. +31).  K is pipelined through STAGES smem stages with full/empty mbarriers;
+// tcgen05.commit releases a stage back to the producer and finally signals the epilogue.
+#include "common.cuh"
+
+namespace smaat {
+
+constexpr int TC_BM = 128;  // pixels per CTA (UMMA M)
+constexpr int TC_BK = 32;   // k per stage (one 128-byte swizzle row of fp32)
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// smem matrix descriptor (cute::UMMA::SmemDescriptor layout): addr>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b_format TF32=2
+// [7,10)/[10,13), a_major MN=1 [15], b_major K=0 [16], N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct PwTcParams {
+  const float* scale;
+  const float* shift;
+  float* y;
+  int64_t y_bstride;
+  float* stats;
+  int K, Cout, P, relu;
+};
+
+template <int N_TILE, int STAGES, bool X3>
+struct PwTcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;    // 16 KB: 4 blocks x (32 k-rows x 128 B)
+  static constexpr int B_BYTES = N_TILE * TC_BK * 4;   // N_TILE rows x 128 B
+  static constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int OFF_ALO = A_BYTES;                       // X3 only
+  static constexpr int OFF_B = (X3 ? 2 : 1) * A_BYTES;
+  static constexpr int OFF_BLO = OFF_B + B_BYTES;               // X3 only
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr uint32_t TX_BYTES = A_BYTES + (X3 ? 2 : 1) * B_BYTES;
+};
+
+template <int N_TILE, int STAGES, bool X3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    pw1x1_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_wlo, const PwTcParams p) {
+  using L = PwTcSmem<N_TILE, STAGES, X3>;
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024-byte alignment: the 128B-swizzle atom (8 rows x 128 B) must start on a 1 KB boundary
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* full_bar = bars;                  // [STAGES] TMA bytes landed
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES] MMAs that read the stage retired
+  uint64_t* xform_bar = bars + 2 * STAGES;    // [STAGES] hi/lo split done (X3)
+  uint64_t* tmem_full_bar = bars + 3 * STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int p0 = blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * N_TILE;
+  const int b = blockIdx.z;
+  const int nk = (p.K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+    if (X3) tma_prefetch_desc(&map_wlo);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&xform_bar[s], 128);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)N_TILE)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        unsigned char* st = smem + s * L::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], L::TX_BYTES);
+        const int k0 = i * TC_BK;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_3d(st + j * (TC_BK * 128), &map_x, &full_bar[s], p0 + 32 * j, k0, b);
+        tma_load_2d(st + L::OFF_B, &map_w, &full_bar[s], k0, n0);
+        if (X3) tma_load_2d(st + L::OFF_BLO, &map_wlo, &full_bar[s], k0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(N_TILE);
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(X3 ? &xform_bar[s] : &full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + L::OFF_B;
+        const int kc = min(TC_BK, p.K - i * TC_BK);
+        const int nmma = (kc + 7) >> 3;
+        for (int kk = 0; kk < nmma; ++kk) {
+          // A (MN-major, SW128): 8 k-rows = one 1 KB atom; 32-pixel blocks 4 KB apart (LBO)
+          const uint64_t ad = make_smem_desc(a_addr + kk * 1024, TC_BK * 128, 1024);
+          // B (K-major, SW128): 8 tf32 = 32 B along the swizzled 128 B row; 8-row groups 1 KB apart (SBO)
+          const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024);
+          umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          if (X3) {
+            const uint64_t ald = make_smem_desc(a_addr + L::OFF_ALO + kk * 1024, TC_BK * 128, 1024);
+            const uint64_t bld = make_smem_desc(a_addr + L::OFF_BLO + kk * 32, 16, 1024);
+            umma_tf32(tmem_base, ald, bd, idesc, 1u);
+            umma_tf32(tmem_base, ad, bld, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // implicit tcgen05.fence::before_thread_sync
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== warps 2..5: transform (X3) then epilogue =====
+    const int et = threadIdx.x - 64;  // 0..127
+    if (X3) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        float4* a4 = reinterpret_cast<float4*>(smem + s * L::STAGE_BYTES);
+        float4* l4 = reinterpret_cast<float4*>(smem + s * L::STAGE_BYTES + L::OFF_ALO);
+#pragma unroll
+        for (int it = 0; it < L::A_BYTES / 16 / 128; ++it) {
+          const int idx = et + it * 128;
+          const float4 v = a4[idx];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          a4[idx] = h;
+          l4[idx] = l;
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor-core (async) proxy
+        mbar_arrive(&xform_bar[s]);
+      }
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int pix = p0 + q * 32 + lane;
+    const bool pvalid = pix < p.P;
+    float* ypix = p.y + (int64_t)b * p.y_bstride + pix;
+#pragma unroll 1
+    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int o = n0 + c0 + j;
+        if (o < p.Cout) {  // warp-uniform
+          const float sc = p.scale ? __ldg(p.scale + o) : 1.f;
+          const float sh = p.shift ? __ldg(p.shift + o) : 0.f;
+          const float pre = fmaf(__uint_as_float(r[j]), sc, sh);
+          if (p.stats) {
+            const float m = pvalid ? pre : 0.f;
+            const float s1 = warp_sum(m), s2 = warp_sum(m * m);
+            if (lane == 0) {
+              atomicAdd(p.stats + o, s1);
+              atomicAdd(p.stats + p.Cout + o, s2);
+            }
+          }
+          if (pvalid) ypix[(int64_t)o * p.P] = p.relu ? fmaxf(pre, 0.f) : pre;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)N_TILE) : "memory");
+  }
+}
+
+template <int N_TILE, int STAGES, bool X3>
+static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mwl, const PwTcParams& p, int B,
+                     cudaStream_t st) {
+  using L = PwTcSmem<N_TILE, STAGES, X3>;
+  auto kern = pw1x1_tc_kernel<N_TILE, STAGES, X3>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "pw1x1(tc): smem attribute (%d B): %s", L::TOTAL, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  dim3 grid(ceil_div(p.P, TC_BM), ceil_div(p.Cout, N_TILE), B);
+  kern<<<grid, TC_THREADS, L::TOTAL, st>>>(mx, mw, mwl, p);
+  SMAAT_LAUNCH_CHECK("smaat_pw1x1_fwd(tc)");
+  return SMAAT_OK;
+}
+
+bool pw1x1_tc_eligible(const float* x, const float* w, const float* w_lo, int K, int Cout, int P) {
+  return (P % 4 == 0) && (K % 4 == 0) && aligned16(x) && aligned16(w) && (w_lo == nullptr || aligned16(w_lo)) && Cout >= 8;
+}
+
+int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const float* scale, const float* shift, float* y,
+                    int64_t y_bstride, float* stats, int B, int K, int Cout, int P, int relu, bool x3, cudaStream_t st) {
+  SMAAT_REQUIRE(pw1x1_tc_eligible(x, w, w_lo, K, Cout, P), "pw1x1(tc): needs P %% 4 == 0, K %% 4 == 0 and 16-byte aligned x/w");
+  SMAAT_REQUIRE(!x3 || w_lo, "pw1x1(tc): TF32X3 needs w_lo (see smaat_split_tf32)");
+  SMAAT_REQUIRE(B <= 65535 && ceil_div(Cout, 64) <= 65535, "pw1x1(tc): grid too large");
+  const int n_tile = (Cout > 128 && !x3) ? 256 : (Cout > 64 ? 128 : 64);
+
+  CUtensorMap mx, mw, mwl;
+  {
+    const uint64_t dims[3] = {(uint64_t)P, (uint64_t)K, (uint64_t)B};
+    const uint64_t str[3] = {0, (uint64_t)P * 4, (uint64_t)K * P * 4};
+    const uint32_t box[3] = {32u, (uint32_t)TC_BK, 1u};
+    int r = make_tmap_f32(&mx, x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "pw1x1(x)");
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)Cout};
+    const uint64_t str[2] = {0, (uint64_t)K * 4};
+    const uint32_t box[2] = {(uint32_t)TC_BK, (uint32_t)n_tile};
+    int r = make_tmap_f32(&mw, w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "pw1x1(w)");
+    if (r) return r;
+    mwl = mw;
+    if (x3) {
+      r = make_tmap_f32(&mwl, w_lo, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "pw1x1(w_lo)");
+      if (r) return r;
+    }
+  }
+  PwTcParams p;
+  p.scale = scale; p.shift = shift; p.y = y; p.y_bstride = y_bstride; p.stats = stats;
+  p.K = K; p.Cout = Cout; p.P = P; p.relu = relu;
+
+  // stage counts chosen so that >= 2 CTAs fit per SM where the tile allows it (227 KB smem, 512 TMEM columns)
+  if (x3) {
+    if (n_tile == 128) return launch_tc<128, 3, true>(mx, mw, mwl, p, B, st);
+    return launch_tc<64, 2, true>(mx, mw, mwl, p, B, st);
+  }
+  if (n_tile == 256) return launch_tc<256, 2, false>(mx, mw, mwl, p, B, st);
+  if (n_tile == 128) return launch_tc<128, 2, false>(mx, mw, mwl, p, B, st);
+  return launch_tc<64, 3, false>(mx, mw, mwl, p, B, st);
+}
+
+}  // namespace smaat

@@ -1,0 +1,262 @@
+"""Drop-in nn.Module replacements for the SmaAt-UNet hot-path blocks.
+
+Host-side mirror of the reference's class interface: same class names,
+constructor signatures, forward signatures and ``state_dict`` keys as
+
+* ``models/layers.py``: DepthwiseSeparableConv (:34-50), ChannelAttention (:90-111),
+  SpatialAttention (:114-129), CBAM (:132-141)
+* ``models/unet_parts_depthwise_separable.py``: DoubleConvDS (:10-39), DownDS (:42-53), UpDS (:56-86)
+* ``models/unet_parts.py``: OutConv (:67-73)
+
+so checkpoints trained with the reference load unchanged (``calc_metrics_test_set.py:114``).
+The parameter containers are ordinary torch modules (``nn.Conv2d`` / ``nn.BatchNorm2d`` /
+``nn.Linear`` -> identical default initialisation and key names) but their ``forward`` is
+never called: all arithmetic runs in libsmaat_b200.so (sm_100a kernels) through ``ops``.
+There is no PyTorch / CPU fallback; unsupported requests raise.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+def _versions(*tensors):
+    return tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+
+
+def _no_autograd(mod, *inputs):
+    if torch.is_grad_enabled() and mod.training:
+        raise NotImplementedError(
+            f"{type(mod).__name__}: train-mode forward with autograd is not implemented in this build of "
+            "smaat_unet_b200 (forward/eval only). Call .eval() and/or torch.no_grad(); no PyTorch fallback is provided.")
+
+
+class DepthwiseSeparableConv(nn.Module):
+    """models/layers.py:34-50 -- depthwise(k x k, groups=Cin, kpl outputs per channel) then pointwise 1x1."""
+
+    def __init__(self, in_channels, output_channels, kernel_size, padding=0, kernels_per_layer=1):
+        super().__init__()
+        self.depthwise = nn.Conv2d(in_channels, in_channels * kernels_per_layer, kernel_size=kernel_size,
+                                   padding=padding, groups=in_channels)
+        self.pointwise = nn.Conv2d(in_channels * kernels_per_layer, output_channels, kernel_size=1)
+        self.kernels_per_layer = kernels_per_layer
+        self._wsplit = None
+        self._wsplit_key = None
+
+    def _check(self):
+        if self.depthwise.kernel_size != (3, 3) or self.depthwise.padding != (1, 1):
+            raise NotImplementedError("smaat_unet_b200 implements the depthwise conv the reference uses: 3x3, padding=1 "
+                                      "(parts_ds.py:18-33)")
+
+    def pw_split(self):
+        """(hi, lo) tf32 split of the pointwise weight, cached on the parameter's version counter."""
+        w = self.pointwise.weight
+        key = _versions(w)
+        if self._wsplit_key != key:
+            with torch.no_grad():
+                self._wsplit = ops.split_tf32(w.detach().view(w.shape[0], -1))
+            self._wsplit_key = key
+        return self._wsplit
+
+    def run(self, x, x1=None, scale=None, shift=None, relu=False, in_scale=None, in_shift=None, stats=None):
+        """dw -> pw with the pw epilogue y = act(scale * acc + shift).  scale/shift None => (1, pointwise.bias)."""
+        self._check()
+        d = ops.dw3x3(x, self.depthwise.weight.detach(), self.depthwise.bias.detach() if self.depthwise.bias is not None else None,
+                      self.kernels_per_layer, x1=x1, in_scale=in_scale, in_shift=in_shift)
+        if shift is None:
+            shift = self.pointwise.bias.detach() if self.pointwise.bias is not None else None
+        mode = ops.get_pointwise_mode()
+        split = self.pw_split() if mode == "tf32x3" else None
+        return ops.pw1x1(d, self.pointwise.weight.detach(), scale, shift, relu, mode=mode, w_split=split, stats=stats)
+
+    def forward(self, x):
+        _no_autograd(self, x)
+        return self.run(x)
+
+
+class DoubleConvDS(nn.Module):
+    """models/unet_parts_depthwise_separable.py:10-39 -- (DS conv => BN => ReLU) * 2.
+
+    Eval mode runs 4 kernels: dw, pw(+folded BN +ReLU), dw, pw(+folded BN +ReLU).
+    """
+
+    def __init__(self, in_channels, out_channels, mid_channels=None, kernels_per_layer=1):
+        super().__init__()
+        if not mid_channels:
+            mid_channels = out_channels
+        self.double_conv = nn.Sequential(
+            DepthwiseSeparableConv(in_channels, mid_channels, kernel_size=3, kernels_per_layer=kernels_per_layer, padding=1),
+            nn.BatchNorm2d(mid_channels),
+            nn.ReLU(inplace=True),
+            DepthwiseSeparableConv(mid_channels, out_channels, kernel_size=3, kernels_per_layer=kernels_per_layer, padding=1),
+            nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+        )
+        self._fold = {}
+
+    def _folded(self, idx):
+        """(scale, shift) of eval BatchNorm idx+1 folded with pointwise bias of DS conv idx; cached."""
+        ds, bn = self.double_conv[idx], self.double_conv[idx + 1]
+        pb = ds.pointwise.bias
+        key = _versions(bn.weight, bn.bias, bn.running_mean, bn.running_var, pb)
+        hit = self._fold.get(idx)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                sc_sh = ops.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                                    pb.detach() if pb is not None else None, bn.eps)
+            self._fold[idx] = (key, sc_sh)
+            hit = self._fold[idx]
+        return hit[1]
+
+    def run(self, x, x1=None):
+        ops._req(x, "input", 4)
+        if self.training:
+            raise NotImplementedError("DoubleConvDS: train-mode (batch-statistics) forward is not implemented in this build")
+        for bn in (self.double_conv[1], self.double_conv[4]):
+            if not bn.track_running_stats or bn.running_mean is None:
+                raise NotImplementedError("BatchNorm2d without running statistics is not supported")
+        s0, t0 = self._folded(0)
+        y = self.double_conv[0].run(x, x1=x1, scale=s0, shift=t0, relu=True)
+        s1, t1 = self._folded(3)
+        return self.double_conv[3].run(y, scale=s1, shift=t1, relu=True)
+
+    def forward(self, x):
+        _no_autograd(self, x)
+        return self.run(x)
+
+
+class DownDS(nn.Module):
+    """models/unet_parts_depthwise_separable.py:42-53 -- MaxPool2d(2) then DoubleConvDS."""
+
+    def __init__(self, in_channels, out_channels, kernels_per_layer=1):
+        super().__init__()
+        self.maxpool_conv = nn.Sequential(
+            nn.MaxPool2d(2),
+            DoubleConvDS(in_channels, out_channels, kernels_per_layer=kernels_per_layer),
+        )
+
+    def forward(self, x):
+        _no_autograd(self, x)
+        return self.maxpool_conv[1].run(ops.maxpool2(x))
+
+
+class UpDS(nn.Module):
+    """models/unet_parts_depthwise_separable.py:56-86 -- upsample x2, pad to the skip, concat, DoubleConvDS.
+
+    The concat is never materialised: the first depthwise kernel reads [skip, up] as a virtual concat.
+    """
+
+    def __init__(self, in_channels, out_channels, bilinear=True, kernels_per_layer=1):
+        super().__init__()
+        self.bilinear = bilinear
+        if bilinear:
+            self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+            self.conv = DoubleConvDS(in_channels, out_channels, in_channels // 2, kernels_per_layer=kernels_per_layer)
+        else:
+            self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
+            self.conv = DoubleConvDS(in_channels, out_channels, kernels_per_layer=kernels_per_layer)
+
+    def forward(self, x1, x2):
+        _no_autograd(self, x1, x2)
+        if not self.bilinear:
+            raise NotImplementedError("UpDS(bilinear=False) (ConvTranspose2d upsampling, parts_ds.py:72-73) is not "
+                                      "implemented in this build; the SmaAt-UNet configs use bilinear=True")
+        up = ops.upsample2x_pad(x1, x2.shape[2], x2.shape[3])
+        return self.conv.run(x2, x1=up)
+
+
+class OutConv(nn.Module):
+    """models/unet_parts.py:67-73 -- 1x1 conv to n_classes."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
+
+    def forward(self, x):
+        _no_autograd(self, x)
+        return ops.outconv(x, self.conv.weight.detach(), self.conv.bias.detach() if self.conv.bias is not None else None)
+
+
+class Flatten(nn.Module):
+    """models/layers.py:85-87 (kept so that MLP indices -- state_dict keys MLP.1 / MLP.3 -- match)."""
+
+    def forward(self, x):
+        return x.view(x.size(0), -1)
+
+
+class ChannelAttention(nn.Module):
+    """models/layers.py:90-111."""
+
+    def __init__(self, input_channels, reduction_ratio=16):
+        super().__init__()
+        self.input_channels = input_channels
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.max_pool = nn.AdaptiveMaxPool2d(1)
+        self.MLP = nn.Sequential(
+            Flatten(),
+            nn.Linear(input_channels, input_channels // reduction_ratio),
+            nn.ReLU(),
+            nn.Linear(input_channels // reduction_ratio, input_channels),
+        )
+
+    def gate(self, x):
+        """sigmoid(MLP(avg) + MLP(max)) as a (B, C) tensor."""
+        avg, mx = ops.cbam_pool(x)
+        l1, l2 = self.MLP[1], self.MLP[3]
+        return ops.cbam_mlp(avg, mx, l1.weight.detach(), l1.bias.detach(), l2.weight.detach(), l2.bias.detach())
+
+    def forward(self, x):
+        _no_autograd(self, x)
+        sc = self.gate(x)
+        ones = torch.ones((x.shape[0], 1, x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)
+        return ops.cbam_scale(x, sc, ones)
+
+
+class SpatialAttention(nn.Module):
+    """models/layers.py:114-129."""
+
+    def __init__(self, kernel_size=7):
+        super().__init__()
+        assert kernel_size in (3, 7), "kernel size must be 3 or 7"
+        padding = 3 if kernel_size == 7 else 1
+        self.conv = nn.Conv2d(2, 1, kernel_size=kernel_size, padding=padding, bias=False)
+        self.bn = nn.BatchNorm2d(1)
+        self._fold = None
+
+    def bn_affine(self):
+        """Device tensor [scale, shift] of the eval-mode BatchNorm2d(1); cached."""
+        if self.training:
+            raise NotImplementedError("SpatialAttention: train-mode (batch-statistics) forward is not implemented in this build")
+        bn = self.bn
+        key = _versions(bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        if self._fold is None or self._fold[0] != key:
+            with torch.no_grad():
+                s, t = ops.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, None, bn.eps)
+                self._fold = (key, torch.cat([s, t]))
+        return self._fold[1]
+
+    def gate(self, x, sc):
+        pooled = ops.cbam_reduce(x, sc)
+        return ops.cbam_gate(pooled, self.conv.weight.detach(), self.bn_affine())
+
+    def forward(self, x):
+        _no_autograd(self, x)
+        ones = torch.ones((x.shape[0], x.shape[1]), device=x.device, dtype=torch.float32)
+        return ops.cbam_scale(x, ones, self.gate(x, ones))
+
+
+class CBAM(nn.Module):
+    """models/layers.py:132-141 -- channel attention then spatial attention, 5 kernels, 4|x| of traffic."""
+
+    def __init__(self, input_channels, reduction_ratio=16, kernel_size=7):
+        super().__init__()
+        self.channel_att = ChannelAttention(input_channels, reduction_ratio=reduction_ratio)
+        self.spatial_att = SpatialAttention(kernel_size=kernel_size)
+
+    def forward(self, x, out=None):
+        _no_autograd(self, x)
+        sc = self.channel_att.gate(x)
+        sa = self.spatial_att.gate(x, sc)
+        return ops.cbam_scale(x, sc, sa, out=out)

@@ -1,0 +1,253 @@
+"""Functional host-side wrappers: torch tensors in, C-ABI calls on the current CUDA stream.
+
+PyTorch is plumbing here (device memory, streams); every byte of arithmetic happens in
+libsmaat_b200.so.  Tensors must be fp32 CUDA tensors, NCHW, dense in (C?, H, W) -- a
+batch stride larger than C*H*W is allowed where the C ABI takes a ``bstride``.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+
+PW_MODES = {"fp32": 0, "tf32": 1, "tf32x3": 2}
+_pw_mode = os.environ.get("SMAAT_PW_MODE", "tf32x3")
+assert _pw_mode in PW_MODES, f"SMAAT_PW_MODE must be one of {list(PW_MODES)}"
+
+
+def set_pointwise_mode(mode: str) -> None:
+    """'tf32x3' (default; tcgen05 3xTF32 split, fp32-grade), 'tf32' (tcgen05 single pass; what
+    cuDNN's allow_tf32=True default gives the reference on a GPU), 'fp32' (CUDA-core exact)."""
+    global _pw_mode
+    if mode not in PW_MODES:
+        raise ValueError(f"pointwise mode must be one of {list(PW_MODES)}")
+    _pw_mode = mode
+
+
+def get_pointwise_mode() -> str:
+    return _pw_mode
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ---- optional per-launch timing (bench.py roofline leg): CUDA events on the launching stream ----
+_prof = None
+
+
+class profile:
+    """Context manager: records (kernel name, algorithmic bytes, flops, start/end CUDA events) for every
+    C-ABI launch made inside it.  ``summary()`` synchronises and aggregates per kernel name."""
+
+    def __enter__(self):
+        global _prof
+        self.records = []
+        _prof = self
+        return self
+
+    def __exit__(self, *exc):
+        global _prof
+        _prof = None
+        return False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, nbytes, flops, e0, e1 in self.records:
+            a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+            a["launches"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["bytes"] += nbytes
+            a["flops"] += flops
+        return agg
+
+
+def _call(name, nbytes, flops, fn, *args):
+    """Invoke one C-ABI entry point on the current stream (optionally bracketed by timing events)."""
+    if _prof is None:
+        _lib.check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(fn(*args), name)
+    e1.record()
+    _prof.records.append((name, int(nbytes), int(flops), e0, e1))
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t, name, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32:
+        raise RuntimeError(f"smaat_unet_b200: {name} must be a float32 CUDA tensor "
+                           f"(got {type(t).__name__} {getattr(t, 'dtype', None)} {getattr(t, 'device', None)}); "
+                           "there is no CPU fallback")
+    if ndim is not None and t.dim() != ndim:
+        raise RuntimeError(f"smaat_unet_b200: {name} must be {ndim}-D, got shape {tuple(t.shape)}")
+    return t
+
+
+def _dense(t, name):
+    _req(t, name)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _nchw_bstride(t, name):
+    """Accept NCHW tensors that are dense in (C,H,W); return (tensor, batch stride in elements)."""
+    _req(t, name, 4)
+    B, Cc, H, W = t.shape
+    st = t.stride()
+    if (st[3] == 1 or W == 1) and (st[2] == W or H == 1) and (st[1] == H * W or Cc == 1) and (B == 1 or st[0] >= Cc * H * W):
+        return t, (st[0] if B > 1 else Cc * H * W)
+    t = t.contiguous()
+    return t, Cc * H * W
+
+
+# ---------------------------------------------------------------------------------------------
+def dw3x3(x, weight, bias, k, x1=None, in_scale=None, in_shift=None, loader=0):
+    """Depthwise 3x3/pad 1 over the virtual concat [x, x1] (layers.py:38-44; parts_ds.py:85)."""
+    x, bs0 = _nchw_bstride(x, "x")
+    B, C0, H, W = x.shape
+    C1, bs1 = 0, 0
+    if x1 is not None:
+        x1, bs1 = _nchw_bstride(x1, "x1")
+        assert x1.shape[0] == B and x1.shape[2:] == x.shape[2:], "concat inputs must agree in B, H, W"
+        C1 = x1.shape[1]
+    w = _dense(weight, "depthwise.weight")
+    assert w.numel() == k * (C0 + C1) * 9, f"depthwise weight {tuple(w.shape)} does not match k*(C0+C1)={k * (C0 + C1)}"
+    y = torch.empty((B, k * (C0 + C1), H, W), device=x.device, dtype=torch.float32)
+    _call("smaat_dw3x3_fwd", 4 * B * H * W * (C0 + C1) * (1 + k), 18 * B * H * W * k * (C0 + C1), _lib.load().smaat_dw3x3_fwd, _ptr(x), C0, bs0, _ptr(x1), C1, bs1, _ptr(w), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
+                                   _ptr(y), B, H, W, k, loader, _stream())
+    return y
+
+
+def tc_eligible(x, w2d) -> bool:
+    K, P = x.shape[1], x.shape[2] * x.shape[3]
+    return bool(_lib.load().smaat_pw1x1_tc_eligible(_ptr(x), _ptr(w2d), K, w2d.shape[0], P))
+
+
+def split_tf32(w):
+    w = _dense(w, "w")
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _call("smaat_split_tf32", 12 * w.numel(), 0, _lib.load().smaat_split_tf32, _ptr(w), _ptr(hi), _ptr(lo), w.numel(), _stream())
+    return hi, lo
+
+
+def pw1x1(x, weight, scale, shift, relu, mode=None, w_split=None, stats=None, out=None):
+    """Pointwise 1x1 + per-channel affine (+ReLU) (layers.py:45,49 + parts_ds.py:25-26).
+
+    weight: (Cout, K[,1,1]).  mode None = module-level default.  w_split = cached (hi, lo) for
+    'tf32x3'.  Falls to the exact CUDA-core kernel for shapes the tcgen05 path does not take.
+    """
+    x = _dense(x, "x")
+    B, K, H, W = x.shape
+    w2d = _dense(weight, "pointwise.weight").view(weight.shape[0], -1)
+    Cout = w2d.shape[0]
+    assert w2d.shape[1] == K, f"pointwise weight {tuple(weight.shape)} does not match K={K}"
+    P = H * W
+    if out is None:
+        out = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.float32)
+        ybs = Cout * P
+    else:
+        out, ybs = _nchw_bstride(out, "out")
+    mode = mode or _pw_mode
+    m = PW_MODES[mode]
+    wlo = None
+    if m != 0 and not tc_eligible(x, w2d):
+        m = 0
+    if m == 2:
+        hi, wlo = w_split if w_split is not None else split_tf32(w2d)
+        w2d = hi
+    _call("smaat_pw1x1_fwd", 4 * B * P * (K + Cout) + 4 * K * Cout, 2 * B * P * K * Cout, _lib.load().smaat_pw1x1_fwd, _ptr(x), _ptr(w2d), _ptr(wlo), _ptr(scale), _ptr(shift), _ptr(out), ybs, _ptr(stats),
+                                           B, K, Cout, P, int(bool(relu)), m, _stream())
+    return out
+
+
+def bn_fold(gamma, beta, running_mean, running_var, conv_bias, eps):
+    """Eval BatchNorm2d -> (scale, shift) for the pw epilogue (parts_ds.py:25,34)."""
+    Cn = gamma.numel()
+    scale = torch.empty(Cn, device=gamma.device, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    _call("smaat_bn_fold", 28 * Cn, 0, _lib.load().smaat_bn_fold, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(conv_bias),
+                                         float(eps), _ptr(scale), _ptr(shift), Cn, _stream())
+    return scale, shift
+
+
+def maxpool2(x):
+    """nn.MaxPool2d(2) (parts_ds.py:48)."""
+    x = _dense(x, "x")
+    B, Cc, H, W = x.shape
+    y = torch.empty((B, Cc, H // 2, W // 2), device=x.device, dtype=torch.float32)
+    _call("smaat_maxpool2_fwd", 4 * B * Cc * (H * W + (H // 2) * (W // 2)), 0, _lib.load().smaat_maxpool2_fwd, _ptr(x), _ptr(y), B * Cc, H, W, _stream())
+    return y
+
+
+def upsample2x_pad(x, Ho, Wo):
+    """nn.Upsample(x2, bilinear, align_corners=True) + F.pad to (Ho, Wo) (parts_ds.py:64,78-81)."""
+    x = _dense(x, "x")
+    B, Cc, H, W = x.shape
+    y = torch.empty((B, Cc, Ho, Wo), device=x.device, dtype=torch.float32)
+    _call("smaat_upsample2x_pad_fwd", 4 * B * Cc * (H * W + Ho * Wo), 0, _lib.load().smaat_upsample2x_pad_fwd, _ptr(x), _ptr(y), Cc * Ho * Wo, B, Cc, H, W, Ho, Wo, _stream())
+    return y
+
+
+def cbam_pool(x):
+    x = _dense(x, "x")
+    B, Cc, H, W = x.shape
+    avg = torch.empty((B, Cc), device=x.device, dtype=torch.float32)
+    mx = torch.empty_like(avg)
+    _call("smaat_cbam_pool_fwd", 4 * B * Cc * H * W, 0, _lib.load().smaat_cbam_pool_fwd, _ptr(x), _ptr(avg), _ptr(mx), B * Cc, H * W, _stream())
+    return avg, mx
+
+
+def cbam_mlp(avg, mx, w1, b1, w2, b2):
+    B, Cc = avg.shape
+    sc = torch.empty_like(avg)
+    _call("smaat_cbam_mlp_fwd", 12 * B * Cc, 0, _lib.load().smaat_cbam_mlp_fwd, _ptr(avg), _ptr(mx), _ptr(_dense(w1, "w1")), _ptr(b1), _ptr(_dense(w2, "w2")), _ptr(b2),
+                                              _ptr(sc), B, Cc, w1.shape[0], _stream())
+    return sc
+
+
+def cbam_reduce(x, sc):
+    x = _dense(x, "x")
+    B, Cc, H, W = x.shape
+    pooled = torch.empty((B, 2, H, W), device=x.device, dtype=torch.float32)
+    _call("smaat_cbam_reduce_fwd", 4 * B * (Cc + 2) * H * W, 0, _lib.load().smaat_cbam_reduce_fwd, _ptr(x), _ptr(sc), _ptr(pooled), B, Cc, H * W, _stream())
+    return pooled
+
+
+def cbam_gate(pooled, wsp, bn_affine, want_raw=False):
+    B, _, H, W = pooled.shape
+    sa = torch.empty((B, 1, H, W), device=pooled.device, dtype=torch.float32)
+    raw = torch.empty_like(sa) if want_raw else None
+    ks = wsp.shape[-1]
+    _call("smaat_cbam_gate_fwd", 12 * B * H * W, 0, _lib.load().smaat_cbam_gate_fwd, _ptr(pooled), _ptr(_dense(wsp, "wsp")), _ptr(bn_affine), _ptr(sa), _ptr(raw), B, H, W, ks,
+                                               _stream())
+    return (sa, raw) if want_raw else sa
+
+
+def cbam_scale(x, sc, sa, out=None):
+    x = _dense(x, "x")
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+        ybs = Cc * H * W
+    else:
+        out, ybs = _nchw_bstride(out, "out")
+    _call("smaat_cbam_scale_fwd", 4 * B * (2 * Cc + 1) * H * W, 0, _lib.load().smaat_cbam_scale_fwd, _ptr(x), _ptr(sc), _ptr(sa), _ptr(out), ybs, B, Cc, H * W, _stream())
+    return out
+
+
+def outconv(x, weight, bias):
+    """OutConv 1x1 (unet_parts.py:70)."""
+    x = _dense(x, "x")
+    B, Cin, H, W = x.shape
+    w = _dense(weight, "weight")
+    ncls = w.shape[0]
+    y = torch.empty((B, ncls, H, W), device=x.device, dtype=torch.float32)
+    _call("smaat_outconv_fwd", 4 * B * (Cin + ncls) * H * W, 2 * B * Cin * ncls * H * W, _lib.load().smaat_outconv_fwd, _ptr(x), _ptr(w), _ptr(bias), _ptr(y), B, Cin, ncls, H * W, _stream())
+    return y

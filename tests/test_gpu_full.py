@@ -1,0 +1,48 @@
+"""-m gpu: full-size checks -- real 288x288 / 576x576 frames vs the torch-functional CPU port of the
+reference (pinned to the golden fixtures in test_oracle_golden.py), plus size-independent
+properties at BASELINE.json's full batch."""
+import numpy as np
+import pytest
+import torch
+
+import smaat_unet_b200 as S
+from oracle import torch_port as TP
+from oracle.cases import cast_sd, fill_schema, smaat_unet_schema
+from tests._util import NET_TOL, assert_close, load_np_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def make_model(seed=5):
+    sd = cast_sd(fill_schema(smaat_unet_schema(12, 1, 2), seed), np.float32)
+    m = load_np_state_dict(S.SmaAt_UNet(12, 1, kernels_per_layer=2), sd).cuda().eval()
+    return m, TP.to_torch_sd(sd)
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("shape", [(2, 12, 288, 288), (1, 12, 576, 576)])
+def test_full_frames_match_cpu_port(shape, mode):
+    m, sd = make_model()
+    x = torch.from_numpy(np.random.default_rng(9).uniform(0, 1, shape).astype(np.float32))
+    with torch.no_grad():
+        ref = TP.smaat_unet_forward(x, sd)
+        S.set_pointwise_mode(mode)
+        try:
+            y = m(x.cuda())
+        finally:
+            S.set_pointwise_mode("tf32x3")
+    assert_close(y, ref.double().numpy(), NET_TOL[mode], f"full {shape} [{mode}]")
+
+
+def test_batch32_samples_are_independent_and_deterministic():
+    """Eval forward has no cross-sample coupling (BN uses running stats, CBAM pools per sample):
+    frame i of a B=32 batch must equal the same frame run alone, bit for bit; and a rerun must be identical."""
+    m, _ = make_model()
+    x = torch.from_numpy(np.random.default_rng(10).uniform(0, 1, (32, 12, 288, 288)).astype(np.float32)).cuda()
+    with torch.no_grad():
+        y = m(x)
+        y2 = m(x)
+        assert torch.equal(y, y2)
+        for i in (0, 17, 31):
+            assert torch.equal(m(x[i:i + 1]), y[i:i + 1])
+    assert torch.isfinite(y).all()

@@ -1,0 +1,192 @@
+"""-m gpu: every kernel behind the C ABI vs the numpy oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+import smaat_unet_b200 as S
+from oracle import smaat_oracle as O
+from smaat_unet_b200 import ops
+from tests._util import PW_TOL, assert_close, dev
+
+pytestmark = pytest.mark.gpu
+RNG = np.random.default_rng(1234)
+
+
+def rnd(*shape, lo=-1.0, hi=1.0):
+    return RNG.uniform(lo, hi, shape).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------ depthwise
+DW_CASES = [
+    # B, C0, C1, H, W, k, loaders
+    (2, 5, 0, 9, 11, 1, (1,)),          # W % 4 != 0 -> LDG only, ragged tiles
+    (2, 6, 0, 12, 8, 2, (1, 2)),
+    (1, 4, 0, 7, 5, 3, (1,)),           # generic k
+    (2, 3, 5, 16, 20, 2, (1, 2)),       # virtual concat
+    (1, 8, 0, 18, 18, 2, (1,)),         # the 18x18 layers (72-byte rows: no TMA)
+    (2, 4, 0, 36, 36, 2, (1, 2)),
+    (1, 3, 0, 72, 72, 2, (1, 2)),
+    (1, 2, 2, 144, 144, 2, (1, 2)),
+    (1, 3, 0, 288, 288, 2, (1, 2)),
+    (1, 2, 0, 100, 148, 1, (1, 2)),     # W = 4*37: no nice divisor -> 64-wide tiles with a ragged edge
+    (1, 2, 0, 40, 576, 2, (1, 2)),
+]
+
+
+@pytest.mark.parametrize("case", DW_CASES)
+def test_dw3x3_matches_oracle(case):
+    B, C0, C1, H, W, k, loaders = case
+    C = C0 + C1
+    x = rnd(B, C, H, W)
+    w = rnd(k * C, 1, 3, 3)
+    b = rnd(k * C)
+    ref = O.depthwise3x3(x.astype(np.float64), w, b, k)
+    x0 = dev(x[:, :C0])
+    x1 = dev(x[:, C0:]) if C1 else None
+    outs = []
+    for ld in loaders:
+        y = ops.dw3x3(x0, dev(w), dev(b), k, x1=x1, loader=ld)
+        torch.cuda.synchronize()
+        assert_close(y, ref, 2e-6, f"dw3x3 loader={ld} {case}")
+        outs.append(y)
+    if len(outs) == 2:   # TMA-staged and LDG-staged tiles must agree bit for bit
+        assert torch.equal(outs[0], outs[1])
+    y = ops.dw3x3(x0, dev(w), None, k, x1=x1)      # no bias
+    assert_close(y, O.depthwise3x3(x.astype(np.float64), w, None, k), 2e-6, "dw3x3 no-bias")
+
+
+@pytest.mark.parametrize("loader", [1, 2])
+def test_dw3x3_prologue_bn_relu_then_zero_pad(loader):
+    B, C, H, W, k = 2, 6, 12, 16, 2
+    x, w, b = rnd(B, C, H, W), rnd(k * C, 1, 3, 3), rnd(k * C)
+    s, t = rnd(C, lo=0.5, hi=1.5), rnd(C)
+    act = np.maximum(x.astype(np.float64) * s[None, :, None, None] + t[None, :, None, None], 0)
+    ref = O.depthwise3x3(act, w, b, k)
+    y = ops.dw3x3(dev(x), dev(w), dev(b), k, in_scale=dev(s), in_shift=dev(t), loader=loader)
+    assert_close(y, ref, 2e-6, "dw3x3 prologue")
+
+
+def test_dw3x3_batch_strided_input():
+    # reading a channel slice of a wider tensor through the batch stride (no copy)
+    B, Cw, C, H, W = 2, 10, 4, 8, 8
+    wide = dev(rnd(B, Cw, H, W))
+    x = wide[:, 2:2 + C]
+    w, b = rnd(2 * C, 1, 3, 3), rnd(2 * C)
+    ref = O.depthwise3x3(x.double().cpu().numpy(), w, b, 2)
+    for ld in (1, 2):
+        assert_close(ops.dw3x3(x, dev(w), dev(b), 2, loader=ld), ref, 2e-6, f"dw3x3 strided loader={ld}")
+
+
+# ------------------------------------------------------------------------------ pointwise
+PW_CASES = [
+    # B, K, Cout, H, W
+    (2, 24, 64, 16, 16),      # inc.0 shape class (single k-chunk, K < 32)
+    (1, 128, 64, 32, 32),     # inc.3 / up4.3
+    (2, 128, 128, 16, 24),
+    (1, 256, 128, 16, 16),
+    (1, 256, 256, 12, 12),    # N_TILE 256, P = 144 (ragged M tile)
+    (2, 512, 256, 8, 8),      # P = 64 < 128
+    (1, 1024, 512, 18, 18),   # down4 shape: P = 324, two N tiles
+    (1, 2048, 512, 6, 6),     # up1.0 K
+    (1, 40, 24, 8, 12),       # K % 32 != 0 tail, Cout < N_TILE
+    (2, 16, 16, 5, 7),        # P % 4 != 0 -> exact CUDA-core kernel in every mode
+]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "tf32x3"])
+@pytest.mark.parametrize("case", PW_CASES)
+def test_pw1x1_matches_oracle(case, mode):
+    B, K, Cout, H, W = case
+    x, w = rnd(B, K, H, W), rnd(Cout, K, 1, 1, lo=-0.2, hi=0.2)
+    scale, shift = rnd(Cout, lo=0.5, hi=1.5), rnd(Cout)
+    acc = O.pointwise1x1(x.astype(np.float64), w, None)
+    ref = np.maximum(acc * scale[None, :, None, None] + shift[None, :, None, None], 0)
+    y = ops.pw1x1(dev(x), dev(w), dev(scale), dev(shift), True, mode=mode)
+    torch.cuda.synchronize()
+    assert_close(y, ref, PW_TOL[mode], f"pw1x1 {mode} {case}")
+    # no affine, no relu: plain conv + nothing
+    y2 = ops.pw1x1(dev(x), dev(w), None, None, False, mode=mode)
+    assert_close(y2, acc, PW_TOL[mode], f"pw1x1 plain {mode} {case}")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+def test_pw1x1_stats_and_strided_output(mode):
+    B, K, Cout, H, W = 2, 64, 48, 12, 12
+    x, w, bias = rnd(B, K, H, W), rnd(Cout, K, 1, 1, lo=-0.3, hi=0.3), rnd(Cout)
+    pre = O.pointwise1x1(x.astype(np.float64), w, bias)
+    stats = torch.zeros(2 * Cout, device="cuda")
+    wide = torch.zeros(B, Cout + 8, H, W, device="cuda")
+    out = wide[:, 8:]
+    ops.pw1x1(dev(x), dev(w), None, dev(bias), False, mode=mode, stats=stats, out=out)
+    assert_close(out, pre, PW_TOL[mode], "pw1x1 strided out")
+    assert float(wide[:, :8].abs().max()) == 0.0
+    assert_close(stats[:Cout], pre.sum(axis=(0, 2, 3)), 1e-4, "channel sums")
+    assert_close(stats[Cout:], (pre ** 2).sum(axis=(0, 2, 3)), 1e-4, "channel sums of squares")
+
+
+def test_split_tf32_is_exact():
+    w = dev(rnd(1000))
+    hi, lo = ops.split_tf32(w)
+    assert torch.equal(hi + lo, w)
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
+# ------------------------------------------------------------------------------ glue
+@pytest.mark.parametrize("shape", [(2, 3, 8, 8), (1, 2, 13, 18), (2, 4, 36, 36), (1, 2, 7, 9), (1, 2, 288, 288)])
+def test_maxpool2(shape):
+    x = rnd(*shape)
+    y = ops.maxpool2(dev(x))
+    assert np.array_equal(y.cpu().numpy(), O.maxpool2(x))       # bit-exact: pure selection
+
+
+@pytest.mark.parametrize("case", [((2, 3, 6, 8), 12, 16), ((1, 2, 4, 6), 9, 13), ((1, 2, 18, 18), 36, 36), ((1, 1, 1, 1), 2, 2),
+                                  ((1, 2, 5, 5), 11, 10)])
+def test_upsample2x_pad(case):
+    shape, Ho, Wo = case
+    x = rnd(*shape)
+    ref = O.pad_to(O.upsample_bilinear2x(x.astype(np.float64)), Ho, Wo)
+    assert_close(ops.upsample2x_pad(dev(x), Ho, Wo), ref, 2e-6, f"upsample {case}")
+
+
+@pytest.mark.parametrize("case", [(2, 64, 1, 16, 16), (1, 64, 5, 8, 12), (1, 64, 21, 9, 7), (2, 16, 2, 6, 6)])
+def test_outconv(case):
+    B, Cin, ncls, H, W = case
+    x, w, b = rnd(B, Cin, H, W), rnd(ncls, Cin, 1, 1, lo=-0.3, hi=0.3), rnd(ncls)
+    assert_close(ops.outconv(dev(x), dev(w), dev(b)), O.pointwise1x1(x.astype(np.float64), w, b), 1e-5, f"outconv {case}")
+
+
+def test_bn_fold():
+    C = 70
+    g, b, rm, rv, cb = rnd(C, lo=0.5, hi=1.5), rnd(C), rnd(C), rnd(C, lo=0.5, hi=1.5), rnd(C)
+    s, t = ops.bn_fold(dev(g), dev(b), dev(rm), dev(rv), dev(cb), 1e-5)
+    es = g.astype(np.float64) / np.sqrt(rv.astype(np.float64) + 1e-5)
+    assert_close(s, es, 1e-6, "bn scale")
+    assert_close(t, b + (cb.astype(np.float64) - rm) * es, 1e-6, "bn shift")
+
+
+# ------------------------------------------------------------------------------ CBAM pieces
+@pytest.mark.parametrize("shape", [(2, 32, 14, 10), (1, 64, 9, 9), (2, 16, 72, 72), (1, 8, 36, 36), (1, 4, 288, 288), (2, 32, 18, 18)])
+def test_cbam_pool_reduce_scale(shape):
+    B, C, H, W = shape
+    x = rnd(*shape)
+    avg, mx = ops.cbam_pool(dev(x))
+    assert_close(avg, x.astype(np.float64).mean(axis=(2, 3)), 1e-5, "cbam avg")
+    assert np.array_equal(mx.cpu().numpy(), x.max(axis=(2, 3)))
+    sc = rnd(B, C, lo=0.1, hi=1.0)
+    xs = x.astype(np.float64) * sc[:, :, None, None]
+    pooled = ops.cbam_reduce(dev(x), dev(sc))
+    assert_close(pooled[:, 0], xs.mean(axis=1), 1e-5, "cbam channel mean")
+    assert_close(pooled[:, 1], xs.max(axis=1), 1e-6, "cbam channel max")
+    sa = rnd(B, 1, H, W, lo=0.1, hi=1.0)
+    assert_close(ops.cbam_scale(dev(x), dev(sc), dev(sa)), xs * sa, 1e-6, "cbam scale")
+
+
+@pytest.mark.parametrize("ks", [3, 7])
+def test_cbam_gate(ks):
+    B, H, W = 2, 37, 45
+    pooled, w = rnd(B, 2, H, W), rnd(1, 2, ks, ks, lo=-0.3, hi=0.3)
+    aff = np.array([1.3, -0.2], dtype=np.float32)
+    a = O.conv2d_same(pooled.astype(np.float64), w, ks // 2)
+    sa, raw = ops.cbam_gate(dev(pooled), dev(w), dev(aff), want_raw=True)
+    assert_close(raw, a, 1e-5, "gate conv")
+    assert_close(sa, O.sigmoid(a * 1.3 - 0.2), 1e-5, "gate sigmoid")
