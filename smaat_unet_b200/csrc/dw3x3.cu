@@ -3,10 +3,11 @@
 // Replaces DepthwiseSeparableConv.depthwise (reference models/layers.py:38-44,48).
 // HBM-bound: algorithmic bytes = 4*B*H*W*Cin*(1+k).  One CTA owns one
 // TH x TW output tile of one (b, cin) plane:
-//   * the (TH+2) x (TW+4) input halo tile is staged in shared memory by ONE TMA
-//     (cp.async.bulk.tensor.4d) whose out-of-bounds zero fill IS the conv's padding=1;
+//   * the (TH+2) x (TW+8) input halo tile is staged in shared memory by ONE TMA
+//     (cp.async.bulk.tensor.4d) whose out-of-bounds zero fill IS the conv's padding=1; the box
+//     starts at column x0-4 because the inner TMA coordinate must be 16-byte aligned;
 //   * each thread walks an RH-row strip of 4 output columns with a 3-row register window
-//     (1 LDS.128 + 1 LDS.64 per input row), producing k output planes, 128-bit stores;
+//     (1 LDS.128 + 2 LDS.32 per input row), producing k output planes, 128-bit stores;
 //   * many small CTAs per SM (<= ~14 KB smem each) keep enough bytes in flight to cover
 //     HBM latency without an intra-CTA pipeline.
 // The input may be the virtual concat of two tensors (UpDS: cat([skip, up]), parts_ds.py:85)
@@ -61,13 +62,13 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __grid_constant__ CUte
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
                 "r"(smem_u32(tile)),
-            "l"(reinterpret_cast<uint64_t>(&map0)), "r"(smem_u32(&bar)), "r"(x0 - 1), "r"(y0 - 1), "r"(c), "r"(b)
+            "l"(reinterpret_cast<uint64_t>(&map0)), "r"(smem_u32(&bar)), "r"(x0 - 4), "r"(y0 - 1), "r"(c), "r"(b)
             : "memory");
       else
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
                 "r"(smem_u32(tile)),
-            "l"(reinterpret_cast<uint64_t>(&map1)), "r"(smem_u32(&bar)), "r"(x0 - 1), "r"(y0 - 1), "r"(c - p.C0), "r"(b)
+            "l"(reinterpret_cast<uint64_t>(&map1)), "r"(smem_u32(&bar)), "r"(x0 - 4), "r"(y0 - 1), "r"(c - p.C0), "r"(b)
             : "memory");
     }
   } else {
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __grid_constant__ CUte
     }
     for (int i = tid; i < BW * BH; i += blockDim.x) {
       const int r = i / BW, cc = i - r * BW;
-      const int gy = y0 - 1 + r, gx = x0 - 1 + cc;
+      const int gy = y0 - 1 + r, gx = x0 - 4 + cc;
       float v = 0.f;
       if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
         v = __ldg(src + (int64_t)gy * p.W + gx);
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __grid_constant__ CUte
       const float s = __ldg(p.in_scale + c), t = __ldg(p.in_shift + c);
       for (int i = tid; i < BW * BH; i += blockDim.x) {
         const int r = i / BW, cc = i - r * BW;
-        const int gy = y0 - 1 + r, gx = x0 - 1 + cc;
+        const int gy = y0 - 1 + r, gx = x0 - 4 + cc;
         const bool inb = (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W);
         tile[i] = inb ? fmaxf(fmaf(tile[i], s, t), 0.f) : 0.f;
       }
@@ -142,20 +143,19 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __grid_constant__ CUte
         br[0] = p.bias ? __ldg(p.bias + o) : 0.f;
       }
       float win[3][6];
-      const float* trow = tile + row0 * BW + col;
+      // smem column of global x is x - (x0 - 4): the 4 outputs at col..col+3 read smem cols col+3..col+8
+      const float* trow = tile + row0 * BW + col + 3;
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const float4 a = *reinterpret_cast<const float4*>(trow + r * BW);
-        const float2 c2 = *reinterpret_cast<const float2*>(trow + r * BW + 4);
-        win[r][0] = a.x; win[r][1] = a.y; win[r][2] = a.z; win[r][3] = a.w; win[r][4] = c2.x; win[r][5] = c2.y;
+        const float4 a = *reinterpret_cast<const float4*>(trow + r * BW + 1);
+        win[r][0] = trow[r * BW]; win[r][1] = a.x; win[r][2] = a.y; win[r][3] = a.z; win[r][4] = a.w; win[r][5] = trow[r * BW + 5];
       }
 #pragma unroll
       for (int i = 0; i < RH; ++i) {
         {
-          const float4 a = *reinterpret_cast<const float4*>(trow + (i + 2) * BW);
-          const float2 c2 = *reinterpret_cast<const float2*>(trow + (i + 2) * BW + 4);
+          const float4 a = *reinterpret_cast<const float4*>(trow + (i + 2) * BW + 1);
           float* wl = win[(i + 2) % 3];
-          wl[0] = a.x; wl[1] = a.y; wl[2] = a.z; wl[3] = a.w; wl[4] = c2.x; wl[5] = c2.y;
+          wl[0] = trow[(i + 2) * BW]; wl[1] = a.x; wl[2] = a.y; wl[3] = a.z; wl[4] = a.w; wl[5] = trow[(i + 2) * BW + 5];
         }
         const int gy = y0 + row0 + i;
         if (gy < p.H) {
@@ -279,7 +279,7 @@ extern "C" int smaat_dw3x3_fwd(const float* x0, int C0, int64_t x0_bstride, cons
   p.B = B; p.H = H; p.W = W; p.k = k;
   int rh;
   pick_tile(H, W, &p.TW, &p.TH, &rh);
-  p.BW = p.TW + 4;
+  p.BW = p.TW + 8;  // box starts at x0-4: TMA needs a 16-byte aligned inner coordinate (measured: x0-1 traps)
   p.BH = p.TH + 2;
   p.tiles_x = ceil_div(W, p.TW);
   p.tiles_y = ceil_div(H, p.TH);

@@ -8,7 +8,7 @@
 // Mapping (per image b):  D[128 pixels x N_TILE channels] += A[128 px x 8] * B[N_TILE x 8]^T
 //   A = activations X[b] ([K][P], pixels contiguous)  -> "MN-major" smem operand: the NCHW
 //       tensor is consumed as it lies in HBM, no transpose, TMA boxes of 32 k-rows x 32 px
-//       with 128B swizzle (4 boxes = 128 pixels);
+//       with the 128B/32B-atom swizzle MN-major tf32 requires (4 boxes = 128 pixels);
 //   B = weights W ([Cout][K], K contiguous)           -> K-major operand, one TMA box
 //       of N_TILE rows x 32 k with 128B swizzle;
 //   D in TMEM: lane = pixel, column = output channel, so tcgen05.ld.32x32b hands every warp
@@ -22,6 +22,8 @@
 // elected lane), warps 2-5 = [X3: hi/lo transform] + epilogue (warp w owns TMEM lanes
 // 32*(w%4) .. +31).  K is pipelined through STAGES smem stages with full/empty mbarriers;
 // tcgen05.commit releases a stage back to the producer and finally signals the epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace smaat {
@@ -34,14 +36,17 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // smem matrix descriptor (cute::UMMA::SmemDescriptor layout): addr>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64): 2 = SWIZZLE_128B (16-byte chunks,
+// 8-row atom), 1 = SWIZZLE_128B_BASE32B (32-byte chunks, 4-row atom) -- the ONLY swizzled
+// layout the hardware accepts for MN-major 32-bit (tf32) operands.
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fffu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -72,6 +77,7 @@ struct PwTcParams {
   int64_t y_bstride;
   float* stats;
   int K, Cout, P, relu;
+  uint32_t a_layout, a_sbo, a_lbo;  // A-operand descriptor fields (defaults below; SMAAT_DBG_* env overrides for bring-up)
 };
 
 template <int N_TILE, int STAGES, bool X3>
@@ -162,14 +168,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int kc = min(TC_BK, p.K - i * TC_BK);
         const int nmma = (kc + 7) >> 3;
         for (int kk = 0; kk < nmma; ++kk) {
-          // A (MN-major, SW128): 8 k-rows = one 1 KB atom; 32-pixel blocks 4 KB apart (LBO)
-          const uint64_t ad = make_smem_desc(a_addr + kk * 1024, TC_BK * 128, 1024);
+          // A (MN-major tf32, SW128 with 32 B atoms): one k-row = 128 B of pixels; 4-row swizzle groups
+          // 512 B apart (SBO), 8 k-rows per MMA = +1 KB per step; 32-pixel blocks 4 KB apart (LBO)
+          const uint64_t ad = make_smem_desc(a_addr + kk * 1024, p.a_lbo, p.a_sbo, p.a_layout);
           // B (K-major, SW128): 8 tf32 = 32 B along the swizzled 128 B row; 8-row groups 1 KB apart (SBO)
-          const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, LAYOUT_SW128);
           umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
           if (X3) {
-            const uint64_t ald = make_smem_desc(a_addr + L::OFF_ALO + kk * 1024, TC_BK * 128, 1024);
-            const uint64_t bld = make_smem_desc(a_addr + L::OFF_BLO + kk * 32, 16, 1024);
+            const uint64_t ald = make_smem_desc(a_addr + L::OFF_ALO + kk * 1024, p.a_lbo, p.a_sbo, p.a_layout);
+            const uint64_t bld = make_smem_desc(a_addr + L::OFF_BLO + kk * 32, 16, 1024, LAYOUT_SW128);
             umma_tf32(tmem_base, ald, bd, idesc, 1u);
             umma_tf32(tmem_base, ad, bld, idesc, 1u);
           }
@@ -286,7 +293,9 @@ int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const flo
     const uint64_t dims[3] = {(uint64_t)P, (uint64_t)K, (uint64_t)B};
     const uint64_t str[3] = {0, (uint64_t)P * 4, (uint64_t)K * P * 4};
     const uint32_t box[3] = {32u, (uint32_t)TC_BK, 1u};
-    int r = make_tmap_f32(&mx, x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "pw1x1(x)");
+    const char* dbg = getenv("SMAAT_DBG_A_TMASWZ");
+    const CUtensorMapSwizzle swz = dbg ? (CUtensorMapSwizzle)atoi(dbg) : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    int r = make_tmap_f32(&mx, x, 3, dims, str, box, swz, "pw1x1(x)");
     if (r) return r;
   }
   {
@@ -304,6 +313,10 @@ int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const flo
   PwTcParams p;
   p.scale = scale; p.shift = shift; p.y = y; p.y_bstride = y_bstride; p.stats = stats;
   p.K = K; p.Cout = Cout; p.P = P; p.relu = relu;
+  p.a_layout = LAYOUT_SW128_BASE32B; p.a_sbo = 512; p.a_lbo = TC_BK * 128;
+  if (const char* e = getenv("SMAAT_DBG_A_LAYOUT")) p.a_layout = (uint32_t)atoi(e);
+  if (const char* e = getenv("SMAAT_DBG_A_SBO")) p.a_sbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("SMAAT_DBG_A_LBO")) p.a_lbo = (uint32_t)atoi(e);
 
   // stage counts chosen so that >= 2 CTAs fit per SM where the tile allows it (227 KB smem, 512 TMEM columns)
   if (x3) {
