@@ -242,6 +242,10 @@ def main():
                 for i in range(3):
                     model(xs[i % 2])
             agg = prof.summary()
+            if os.environ.get("SMAAT_BENCH_LAYERS"):
+                for name, a in prof.summary(by_shape=True).items():
+                    if "[" in name:
+                        print(f"# {name:40s} {a['ms'] / 3:8.3f} ms  {a['bytes'] / a['ms'] / 1e6:7.0f} GB/s  {a['flops'] / a['ms'] / 1e9:7.1f} TF", file=sys.stderr)
         for name, a in agg.items():
             gbs = a["bytes"] / (a["ms"] * 1e-3) / 1e9 if a["ms"] > 0 else 0.0
             kernels[name] = {"launches_per_step": a["launches"] // 3, "ms_per_step": a["ms"] / 3, "algorithmic_GB_per_step": a["bytes"] / 3e9,

@@ -55,36 +55,51 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__
 }
 
 // ---- bilinear x2 (align_corners=True) + zero pad ------------------------------------------------
-// One thread per output element, coalesced stores; the 4 taps come from a 4x smaller source
-// that stays in L1/L2.  Index math follows torch's area_pixel_compute_source_index for
-// align_corners=True: src = dst * (in-1)/(out-1).
+// grid = (row-quads of one plane, C, B): 32-bit index math only; one thread -> 4 consecutive output
+// pixels of one row (one 128-bit store); the 2 source rows / <= 4 source columns it needs come from
+// a 4x smaller plane that stays in L1/L2.  Index math follows torch's area_pixel_compute_source_index
+// for align_corners=True: src = dst * (in-1)/(out-1).
+template <bool VEC>
 __global__ void __launch_bounds__(256) upsample2x_pad_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                             int64_t y_bstride, int B, int C, int H, int W, int Ho, int Wo,
+                                                             int64_t y_bstride, int C, int H, int W, int Ho, int Wo,
                                                              int pad_t, int pad_l, float ry, float rx) {
-  const int64_t total = (int64_t)B * C * Ho * Wo;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % Wo);
-    int64_t t = i / Wo;
-    const int oy = (int)(t % Ho);
-    t /= Ho;
-    const int c = (int)(t % C);
-    const int b = (int)(t / C);
-    const int uy = oy - pad_t, ux = ox - pad_l;
-    float v = 0.f;
-    if (uy >= 0 && uy < 2 * H && ux >= 0 && ux < 2 * W) {
-      const float sy = ry * uy, sx = rx * ux;
-      int y0 = (int)sy, x0 = (int)sx;
-      y0 = min(y0, H - 1);
-      x0 = min(x0, W - 1);
-      const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-      const float ly = sy - y0, lx = sx - x0;
-      const float* src = x + ((int64_t)b * C + c) * H * W;
-      const float v00 = __ldg(src + (int64_t)y0 * W + x0), v01 = __ldg(src + (int64_t)y0 * W + x1);
-      const float v10 = __ldg(src + (int64_t)y1 * W + x0), v11 = __ldg(src + (int64_t)y1 * W + x1);
-      // same association as torch's upsample_bilinear2d: w_y0*(w_x0*v00 + w_x1*v01) + w_y1*(...)
-      v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  const int wq = (Wo + 3) >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Ho * wq) return;
+  const int oy = idx / wq;
+  const int ox0 = (idx - oy * wq) << 2;
+  const int c = blockIdx.y, b = blockIdx.z;
+  const float* src = x + ((int64_t)b * C + c) * H * W;
+  float* dst = y + (int64_t)b * y_bstride + ((int64_t)c * Ho + oy) * Wo + ox0;
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  const int uy = oy - pad_t;
+  if (uy >= 0 && uy < 2 * H) {
+    const float sy = ry * uy;
+    int y0 = min((int)sy, H - 1);
+    const int y1 = min(y0 + 1, H - 1);
+    const float ly = sy - y0;
+    const float* r0 = src + y0 * W;
+    const float* r1 = src + y1 * W;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ux = ox0 + j - pad_l;
+      if (ux >= 0 && ux < 2 * W) {
+        const float sx = rx * ux;
+        const int x0 = min((int)sx, W - 1);
+        const int x1 = min(x0 + 1, W - 1);
+        const float lx = sx - x0;
+        // same association as torch's upsample_bilinear2d: w_y0*(w_x0*v00 + w_x1*v01) + w_y1*(...)
+        o[j] = (1.f - ly) * ((1.f - lx) * __ldg(r0 + x0) + lx * __ldg(r0 + x1)) +
+               ly * ((1.f - lx) * __ldg(r1 + x0) + lx * __ldg(r1 + x1));
+      }
     }
-    y[(int64_t)b * y_bstride + ((int64_t)c * Ho + oy) * Wo + ox] = v;
+  }
+  if (VEC) {
+    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (ox0 + j < Wo) dst[j] = o[j];
   }
 }
 
@@ -191,10 +206,13 @@ extern "C" int smaat_upsample2x_pad_fwd(const float* x, float* y, int64_t y_bstr
   const int pad_t = (Ho - 2 * H) / 2, pad_l = (Wo - 2 * W) / 2;
   const float ry = (2 * H > 1) ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
   const float rx = (2 * W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
-  const int64_t total = (int64_t)B * C * Ho * Wo;
-  const int64_t blocks = ceil_div64(total, 256);
-  const unsigned grid = (unsigned)(blocks < (int64_t)num_sms() * 64 ? blocks : (int64_t)num_sms() * 64);
-  upsample2x_pad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, y_bstride, B, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx);
+  SMAAT_REQUIRE(C <= 65535 && B <= 65535, "upsample2x: C/B too large for grid.y/z");
+  const bool vec = (Wo % 4 == 0) && aligned16(y) && (y_bstride % 4 == 0);
+  dim3 grid(ceil_div(Ho * ceil_div(Wo, 4), 256), C, B);
+  if (vec)
+    upsample2x_pad_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx);
+  else
+    upsample2x_pad_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx);
   SMAAT_LAUNCH_CHECK("smaat_upsample2x_pad_fwd");
   return SMAAT_OK;
 }

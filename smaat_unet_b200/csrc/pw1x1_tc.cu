@@ -7,38 +7,40 @@
 //
 // Mapping (per image b):  D[128 pixels x N_TILE channels] += A[128 px x 8] * B[N_TILE x 8]^T
 //   A = activations X[b] ([K][P], pixels contiguous)  -> "MN-major" smem operand: the NCHW
-//       tensor is consumed as it lies in HBM, no transpose, TMA boxes of 32 k-rows x 32 px
-//       with the 128B/32B-atom swizzle MN-major tf32 requires (4 boxes = 128 pixels);
+//       tensor is consumed as it lies in HBM, no transpose.  TMA boxes of 32 k-rows x 32 px
+//       (4 boxes = 128 pixels) with the 128B-span / 32B-atom swizzle, the only swizzled layout
+//       the hardware takes for MN-major 32-bit operands (UMMA layout type SWIZZLE_128B_BASE32B);
 //   B = weights W ([Cout][K], K contiguous)           -> K-major operand, one TMA box
-//       of N_TILE rows x 32 k with 128B swizzle;
+//       of N_TILE rows x 32 k with the plain 128B swizzle;
 //   D in TMEM: lane = pixel, column = output channel, so tcgen05.ld.32x32b hands every warp
 //       32 consecutive pixels of one channel per register -> fully coalesced NCHW stores with
 //       no smem staging.  kind::tf32, fp32 accumulate.
 // TF32X3 mode (fp32-grade accuracy): activations are split in smem into a tf32 "hi" part and
-// the "lo" remainder by the 4 transform/epilogue warps; weights arrive pre-split; three MMAs
+// the "lo" remainder by 4 transform warps; weights arrive pre-split; three MMAs
 // (hi*hi + lo*hi + hi*lo) per k-step accumulate into the same TMEM tile.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one
-// elected lane), warps 2-5 = [X3: hi/lo transform] + epilogue (warp w owns TMEM lanes
-// 32*(w%4) .. +31).  K is pipelined through STAGES smem stages with full/empty mbarriers;
-// tcgen05.commit releases a stage back to the producer and finally signals the epilogue.
-#include <stdlib.h>
-
+// Persistent, warp-specialised: one CTA per SM loops over output tiles (tile = blockIdx.x +
+// i*gridDim.x; consecutive tiles share the activation tile and differ in the channel tile so the
+// re-read hits L2).  warp 0 = TMA producer (runs ahead across tile boundaries through a
+// STAGES-deep smem ring), warp 1 = TMEM alloc + MMA issuer (one elected lane), warps 2-5 =
+// epilogue (warp w owns TMEM lanes 32*(w%4)..+31), warps 6-9 = hi/lo transform (X3 only).
+// Two accumulator stages in TMEM (2 x N_TILE columns) let the epilogue of tile i overlap the
+// MMAs of tile i+1.  mbarriers: full/empty per smem stage, xform per stage (X3),
+// tmem_full/tmem_empty per accumulator stage; tcgen05.commit releases smem stages and
+// publishes finished accumulators.
 #include "common.cuh"
 
 namespace smaat {
 
-constexpr int TC_BM = 128;  // pixels per CTA (UMMA M)
-constexpr int TC_BK = 32;   // k per stage (one 128-byte swizzle row of fp32)
-constexpr int TC_THREADS = 192;
+constexpr int TC_BM = 128;  // pixels per tile (UMMA M)
+constexpr int TC_BK = 32;   // k per stage (one 128-byte swizzle row of fp32 on the weight side)
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // smem matrix descriptor (cute::UMMA::SmemDescriptor layout): addr>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type [61,64): 2 = SWIZZLE_128B (16-byte chunks,
-// 8-row atom), 1 = SWIZZLE_128B_BASE32B (32-byte chunks, 4-row atom) -- the ONLY swizzled
-// layout the hardware accepts for MN-major 32-bit (tf32) operands.
+// 8-row atom), 1 = SWIZZLE_128B_BASE32B (32-byte chunks, 4-row atom).
 constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
@@ -77,42 +79,47 @@ struct PwTcParams {
   int64_t y_bstride;
   float* stats;
   int K, Cout, P, relu;
-  uint32_t a_layout, a_sbo, a_lbo;  // A-operand descriptor fields (defaults below; SMAAT_DBG_* env overrides for bring-up)
+  int tiles_m, tiles_n, total_tiles;
 };
 
 template <int N_TILE, int STAGES, bool X3>
-struct PwTcSmem {
-  static constexpr int A_BYTES = TC_BM * TC_BK * 4;    // 16 KB: 4 blocks x (32 k-rows x 128 B)
-  static constexpr int B_BYTES = N_TILE * TC_BK * 4;   // N_TILE rows x 128 B
+struct PwTcCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;   // 16 KB: 4 blocks x (32 k-rows x 128 B)
+  static constexpr int B_BYTES = N_TILE * TC_BK * 4;  // N_TILE rows x 128 B
   static constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_BYTES + B_BYTES);
-  static constexpr int OFF_ALO = A_BYTES;                       // X3 only
+  static constexpr int OFF_ALO = A_BYTES;  // X3 only
   static constexpr int OFF_B = (X3 ? 2 : 1) * A_BYTES;
-  static constexpr int OFF_BLO = OFF_B + B_BYTES;               // X3 only
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int OFF_BLO = OFF_B + B_BYTES;  // X3 only
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int AFF_N = 512;                                      // per-channel epilogue affine staged in smem
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 2 * AFF_N * 4 + 1024;  // + alignment slack
   static constexpr uint32_t TX_BYTES = A_BYTES + (X3 ? 2 : 1) * B_BYTES;
+  static constexpr int THREADS = X3 ? 320 : 192;
+  static constexpr int TMEM_COLS = 2 * N_TILE;  // two accumulator stages
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
 template <int N_TILE, int STAGES, bool X3>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
     pw1x1_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_wlo, const PwTcParams p) {
-  using L = PwTcSmem<N_TILE, STAGES, X3>;
-  extern __shared__ unsigned char smem_dyn[];
-  // 1024-byte alignment: the 128B-swizzle atom (8 rows x 128 B) must start on a 1 KB boundary
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  using L = PwTcCfg<N_TILE, STAGES, X3>;
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // 1 KB alignment: swizzle atoms (8 x 128 B for the weights, 4 x 128 B for the activations).  Offset arithmetic
+  // on the __shared__ array (not a uintptr_t round trip) keeps the accesses LDS/STS instead of generic LD/ST.
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
-  uint64_t* full_bar = bars;                  // [STAGES] TMA bytes landed
-  uint64_t* empty_bar = bars + STAGES;        // [STAGES] MMAs that read the stage retired
-  uint64_t* xform_bar = bars + 2 * STAGES;    // [STAGES] hi/lo split done (X3)
-  uint64_t* tmem_full_bar = bars + 3 * STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+  float* aff = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES);  // [2][AFF_N] scale | shift
+  uint64_t* full_bar = bars;                         // [STAGES] TMA bytes landed
+  uint64_t* empty_bar = bars + STAGES;               // [STAGES] MMAs that read the stage retired
+  uint64_t* xform_bar = bars + 2 * STAGES;           // [STAGES] hi/lo split done (X3)
+  uint64_t* tmem_full_bar = bars + 3 * STAGES;       // [2] accumulator complete
+  uint64_t* tmem_empty_bar = bars + 3 * STAGES + 2;  // [2] accumulator drained by the epilogue
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int p0 = blockIdx.x * TC_BM;
-  const int n0 = blockIdx.y * N_TILE;
-  const int b = blockIdx.z;
   const int nk = (p.K + TC_BK - 1) / TC_BK;
 
   if (warp == 0 && lane == 0) {
@@ -124,14 +131,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(&empty_bar[s], 1);
       mbar_init(&xform_bar[s], 128);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)N_TILE)
+                 "r"((uint32_t)L::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // epilogue affine of the channels this CTA can touch (padded with identity), read back as LDS.128 broadcasts
+  for (int c = threadIdx.x; c < L::AFF_N; c += blockDim.x) {
+    aff[c] = (c < p.Cout && p.scale) ? __ldg(p.scale + c) : 1.f;
+    aff[L::AFF_N + c] = (c < p.Cout && p.shift) ? __ldg(p.shift + c) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -141,63 +156,152 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        unsigned char* st = smem + s * L::STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], L::TX_BYTES);
-        const int k0 = i * TC_BK;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int tn = tile % p.tiles_n;
+        const int rest = tile / p.tiles_n;
+        const int tm = rest % p.tiles_m;
+        const int b = rest / p.tiles_m;
+        const int p0 = tm * TC_BM, n0 = tn * N_TILE;
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          unsigned char* st = smem + s * L::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], L::TX_BYTES);
+          const int k0 = i * TC_BK;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_3d(st + j * (TC_BK * 128), &map_x, &full_bar[s], p0 + 32 * j, k0, b);
-        tma_load_2d(st + L::OFF_B, &map_w, &full_bar[s], k0, n0);
-        if (X3) tma_load_2d(st + L::OFF_BLO, &map_wlo, &full_bar[s], k0, n0);
+          for (int j = 0; j < 4; ++j) tma_load_3d(st + j * (TC_BK * 128), &map_x, &full_bar[s], p0 + 32 * j, k0, b);
+          tma_load_2d(st + L::OFF_B, &map_w, &full_bar[s], k0, n0);
+          if (X3) tma_load_2d(st + L::OFF_BLO, &map_wlo, &full_bar[s], k0, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(N_TILE);
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(X3 ? &xform_bar[s] : &full_bar[s], ph);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u;
+        const uint32_t acc_ph = (tcount >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + L::OFF_B;
-        const int kc = min(TC_BK, p.K - i * TC_BK);
-        const int nmma = (kc + 7) >> 3;
-        for (int kk = 0; kk < nmma; ++kk) {
-          // A (MN-major tf32, SW128 with 32 B atoms): one k-row = 128 B of pixels; 4-row swizzle groups
-          // 512 B apart (SBO), 8 k-rows per MMA = +1 KB per step; 32-pixel blocks 4 KB apart (LBO)
-          const uint64_t ad = make_smem_desc(a_addr + kk * 1024, p.a_lbo, p.a_sbo, p.a_layout);
-          // B (K-major, SW128): 8 tf32 = 32 B along the swizzled 128 B row; 8-row groups 1 KB apart (SBO)
-          const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, LAYOUT_SW128);
-          umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
-          if (X3) {
-            const uint64_t ald = make_smem_desc(a_addr + L::OFF_ALO + kk * 1024, p.a_lbo, p.a_sbo, p.a_layout);
-            const uint64_t bld = make_smem_desc(a_addr + L::OFF_BLO + kk * 32, 16, 1024, LAYOUT_SW128);
-            umma_tf32(tmem_base, ald, bd, idesc, 1u);
-            umma_tf32(tmem_base, ad, bld, idesc, 1u);
+        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(X3 ? &xform_bar[s] : &full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + L::OFF_B;
+          const int kc = min(TC_BK, p.K - i * TC_BK);
+          const int nmma = (kc + 7) >> 3;
+          for (int kk = 0; kk < nmma; ++kk) {
+            // A (MN-major tf32, SW128 with 32 B atoms): one k-row = 128 B of pixels; 4-row swizzle groups
+            // 512 B apart (SBO), 8 k-rows per MMA = +1 KB per step; 32-pixel blocks 4 KB apart (LBO)
+            const uint64_t ad = make_smem_desc(a_addr + kk * 1024, TC_BK * 128, 512, LAYOUT_SW128_BASE32B);
+            // B (K-major, SW128): 8 tf32 = 32 B along the swizzled 128 B row; 8-row groups 1 KB apart (SBO)
+            const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, LAYOUT_SW128);
+            umma_tf32(d_tmem, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            if (X3) {
+              const uint64_t ald = make_smem_desc(a_addr + L::OFF_ALO + kk * 1024, TC_BK * 128, 512, LAYOUT_SW128_BASE32B);
+              const uint64_t bld = make_smem_desc(a_addr + L::OFF_BLO + kk * 32, 16, 1024, LAYOUT_SW128);
+              umma_tf32(d_tmem, ald, bd, idesc, 1u);
+              umma_tf32(d_tmem, ad, bld, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[s]);  // implicit tcgen05.fence::before_thread_sync
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== epilogue warps 2..5: TMEM -> registers -> affine/ReLU -> coalesced NCHW stores =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const float act_lo = p.relu ? 0.f : -INFINITY;  // ReLU as a branch-free max()
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const int tn = tile % p.tiles_n;
+      const int rest = tile / p.tiles_n;
+      const int tm = rest % p.tiles_m;
+      const int b = rest / p.tiles_m;
+      const int n0 = tn * N_TILE;
+      const uint32_t acc = tcount & 1u;
+      const uint32_t acc_ph = (tcount >> 1) & 1u;
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      const int pix = tm * TC_BM + q * 32 + lane;
+      const bool pvalid = pix < p.P;
+      float* ypix = p.y + (int64_t)b * p.y_bstride + pix;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        if (n0 + c0 >= p.Cout) break;
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        float scv[32], shv[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 a = *reinterpret_cast<const float4*>(aff + n0 + c0 + 4 * j4);
+          const float4 t = *reinterpret_cast<const float4*>(aff + L::AFF_N + n0 + c0 + 4 * j4);
+          scv[4 * j4] = a.x; scv[4 * j4 + 1] = a.y; scv[4 * j4 + 2] = a.z; scv[4 * j4 + 3] = a.w;
+          shv[4 * j4] = t.x; shv[4 * j4 + 1] = t.y; shv[4 * j4 + 2] = t.z; shv[4 * j4 + 3] = t.w;
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int nch = min(32, p.Cout - (n0 + c0));  // warp-uniform
+        float* yp = ypix + (int64_t)(n0 + c0) * p.P;
+        if (p.stats == nullptr && nch == 32) {
+          // hot path: 5 instructions per channel (FFMA, FMNMX, 64-bit pointer bump, predicated STG), no branches
+          if (pvalid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              *yp = fmaxf(fmaf(__uint_as_float(r[j]), scv[j], shv[j]), act_lo);
+              yp += p.P;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nch) {
+              const float pre = fmaf(__uint_as_float(r[j]), scv[j], shv[j]);
+              if (p.stats) {
+                const float m = pvalid ? pre : 0.f;
+                const float s1 = warp_sum(m), s2 = warp_sum(m * m);
+                if (lane == 0) {
+                  atomicAdd(p.stats + n0 + c0 + j, s1);
+                  atomicAdd(p.stats + p.Cout + n0 + c0 + j, s2);
+                }
+              }
+              if (pvalid) yp[(int64_t)j * p.P] = fmaxf(pre, act_lo);
+            }
           }
         }
-        umma_commit(&empty_bar[s]);  // implicit tcgen05.fence::before_thread_sync
       }
-      umma_commit(tmem_full_bar);
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);  // 128 arrivals release the accumulator stage to the MMA warp
     }
-  } else {
-    // ===== warps 2..5: transform (X3) then epilogue =====
-    const int et = threadIdx.x - 64;  // 0..127
-    if (X3) {
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+  } else if (X3) {
+    // ===== warps 6..9: split the landed activations into tf32 hi (in place) and lo =====
+    const int et = threadIdx.x - 192;  // 0..127
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int i = 0; i < nk; ++i, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
         mbar_wait(&full_bar[s], ph);
         float4* a4 = reinterpret_cast<float4*>(smem + s * L::STAGE_BYTES);
         float4* l4 = reinterpret_cast<float4*>(smem + s * L::STAGE_BYTES + L::OFF_ALO);
 #pragma unroll
-        for (int it = 0; it < L::A_BYTES / 16 / 128; ++it) {
-          const int idx = et + it * 128;
+        for (int itx = 0; itx < L::A_BYTES / 16 / 128; ++itx) {
+          const int idx = et + itx * 128;
           const float4 v = a4[idx];
           float4 h, l;
           h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
@@ -212,58 +316,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_arrive(&xform_bar[s]);
       }
     }
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int pix = p0 + q * 32 + lane;
-    const bool pvalid = pix < p.P;
-    float* ypix = p.y + (int64_t)b * p.y_bstride + pix;
-#pragma unroll 1
-    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int o = n0 + c0 + j;
-        if (o < p.Cout) {  // warp-uniform
-          const float sc = p.scale ? __ldg(p.scale + o) : 1.f;
-          const float sh = p.shift ? __ldg(p.shift + o) : 0.f;
-          const float pre = fmaf(__uint_as_float(r[j]), sc, sh);
-          if (p.stats) {
-            const float m = pvalid ? pre : 0.f;
-            const float s1 = warp_sum(m), s2 = warp_sum(m * m);
-            if (lane == 0) {
-              atomicAdd(p.stats + o, s1);
-              atomicAdd(p.stats + p.Cout + o, s2);
-            }
-          }
-          if (pvalid) ypix[(int64_t)o * p.P] = p.relu ? fmaxf(pre, 0.f) : pre;
-        }
-      }
-    }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)N_TILE) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::TMEM_COLS) : "memory");
   }
 }
 
 template <int N_TILE, int STAGES, bool X3>
-static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mwl, const PwTcParams& p, int B,
-                     cudaStream_t st) {
-  using L = PwTcSmem<N_TILE, STAGES, X3>;
+static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mwl, PwTcParams p, int B, cudaStream_t st) {
+  using L = PwTcCfg<N_TILE, STAGES, X3>;
   auto kern = pw1x1_tc_kernel<N_TILE, STAGES, X3>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -271,8 +335,13 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
     if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "pw1x1(tc): smem attribute (%d B): %s", L::TOTAL, cudaGetErrorString(e));
     attr_done = true;
   }
-  dim3 grid(ceil_div(p.P, TC_BM), ceil_div(p.Cout, N_TILE), B);
-  kern<<<grid, TC_THREADS, L::TOTAL, st>>>(mx, mw, mwl, p);
+  p.tiles_m = ceil_div(p.P, TC_BM);
+  p.tiles_n = ceil_div(p.Cout, N_TILE);
+  const int64_t total = (int64_t)B * p.tiles_m * p.tiles_n;
+  SMAAT_REQUIRE(total < (1ll << 31), "pw1x1(tc): too many tiles");
+  p.total_tiles = (int)total;
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  kern<<<grid, L::THREADS, L::TOTAL, st>>>(mx, mw, mwl, p);
   SMAAT_LAUNCH_CHECK("smaat_pw1x1_fwd(tc)");
   return SMAAT_OK;
 }
@@ -285,7 +354,7 @@ int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const flo
                     int64_t y_bstride, float* stats, int B, int K, int Cout, int P, int relu, bool x3, cudaStream_t st) {
   SMAAT_REQUIRE(pw1x1_tc_eligible(x, w, w_lo, K, Cout, P), "pw1x1(tc): needs P %% 4 == 0, K %% 4 == 0 and 16-byte aligned x/w");
   SMAAT_REQUIRE(!x3 || w_lo, "pw1x1(tc): TF32X3 needs w_lo (see smaat_split_tf32)");
-  SMAAT_REQUIRE(B <= 65535 && ceil_div(Cout, 64) <= 65535, "pw1x1(tc): grid too large");
+  SMAAT_REQUIRE(Cout <= 512, "pw1x1(tc): Cout=%d > 512 (epilogue affine staging)", Cout);
   const int n_tile = (Cout > 128 && !x3) ? 256 : (Cout > 64 ? 128 : 64);
 
   CUtensorMap mx, mw, mwl;
@@ -293,9 +362,7 @@ int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const flo
     const uint64_t dims[3] = {(uint64_t)P, (uint64_t)K, (uint64_t)B};
     const uint64_t str[3] = {0, (uint64_t)P * 4, (uint64_t)K * P * 4};
     const uint32_t box[3] = {32u, (uint32_t)TC_BK, 1u};
-    const char* dbg = getenv("SMAAT_DBG_A_TMASWZ");
-    const CUtensorMapSwizzle swz = dbg ? (CUtensorMapSwizzle)atoi(dbg) : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    int r = make_tmap_f32(&mx, x, 3, dims, str, box, swz, "pw1x1(x)");
+    int r = make_tmap_f32(&mx, x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, "pw1x1(x)");
     if (r) return r;
   }
   {
@@ -313,19 +380,16 @@ int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const flo
   PwTcParams p;
   p.scale = scale; p.shift = shift; p.y = y; p.y_bstride = y_bstride; p.stats = stats;
   p.K = K; p.Cout = Cout; p.P = P; p.relu = relu;
-  p.a_layout = LAYOUT_SW128_BASE32B; p.a_sbo = 512; p.a_lbo = TC_BK * 128;
-  if (const char* e = getenv("SMAAT_DBG_A_LAYOUT")) p.a_layout = (uint32_t)atoi(e);
-  if (const char* e = getenv("SMAAT_DBG_A_SBO")) p.a_sbo = (uint32_t)atoi(e);
-  if (const char* e = getenv("SMAAT_DBG_A_LBO")) p.a_lbo = (uint32_t)atoi(e);
+  p.tiles_m = p.tiles_n = p.total_tiles = 0;
 
-  // stage counts chosen so that >= 2 CTAs fit per SM where the tile allows it (227 KB smem, 512 TMEM columns)
+  // one persistent CTA per SM: the smem ring takes ~192 KB of the 227 KB
   if (x3) {
     if (n_tile == 128) return launch_tc<128, 3, true>(mx, mw, mwl, p, B, st);
-    return launch_tc<64, 2, true>(mx, mw, mwl, p, B, st);
+    return launch_tc<64, 4, true>(mx, mw, mwl, p, B, st);
   }
-  if (n_tile == 256) return launch_tc<256, 2, false>(mx, mw, mwl, p, B, st);
-  if (n_tile == 128) return launch_tc<128, 2, false>(mx, mw, mwl, p, B, st);
-  return launch_tc<64, 3, false>(mx, mw, mwl, p, B, st);
+  if (n_tile == 256) return launch_tc<256, 4, false>(mx, mw, mwl, p, B, st);
+  if (n_tile == 128) return launch_tc<128, 6, false>(mx, mw, mwl, p, B, st);
+  return launch_tc<64, 8, false>(mx, mw, mwl, p, B, st);
 }
 
 }  // namespace smaat

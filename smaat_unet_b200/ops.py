@@ -53,11 +53,12 @@ class profile:
         _prof = None
         return False
 
-    def summary(self):
+    def summary(self, by_shape=False):
         torch.cuda.synchronize()
         agg = {}
         for name, nbytes, flops, e0, e1 in self.records:
-            a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+            key = name if by_shape else name.split("[")[0]
+            a = agg.setdefault(key, {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
             a["launches"] += 1
             a["ms"] += e0.elapsed_time(e1)
             a["bytes"] += nbytes
@@ -68,7 +69,7 @@ class profile:
 def _call(name, nbytes, flops, fn, *args):
     """Invoke one C-ABI entry point on the current stream (optionally bracketed by timing events)."""
     if _prof is None:
-        _lib.check(fn(*args), name)
+        _lib.check(fn(*args), name.split("[")[0])
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -120,7 +121,7 @@ def dw3x3(x, weight, bias, k, x1=None, in_scale=None, in_shift=None, loader=0):
     w = _dense(weight, "depthwise.weight")
     assert w.numel() == k * (C0 + C1) * 9, f"depthwise weight {tuple(w.shape)} does not match k*(C0+C1)={k * (C0 + C1)}"
     y = torch.empty((B, k * (C0 + C1), H, W), device=x.device, dtype=torch.float32)
-    _call("smaat_dw3x3_fwd", 4 * B * H * W * (C0 + C1) * (1 + k), 18 * B * H * W * k * (C0 + C1), _lib.load().smaat_dw3x3_fwd, _ptr(x), C0, bs0, _ptr(x1), C1, bs1, _ptr(w), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
+    _call(f"smaat_dw3x3_fwd[C{C0 + C1}_S{H}]", 4 * B * H * W * (C0 + C1) * (1 + k), 18 * B * H * W * k * (C0 + C1), _lib.load().smaat_dw3x3_fwd, _ptr(x), C0, bs0, _ptr(x1), C1, bs1, _ptr(w), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
                                    _ptr(y), B, H, W, k, loader, _stream())
     return y
 
@@ -162,7 +163,7 @@ def pw1x1(x, weight, scale, shift, relu, mode=None, w_split=None, stats=None, ou
     if m == 2:
         hi, wlo = w_split if w_split is not None else split_tf32(w2d)
         w2d = hi
-    _call("smaat_pw1x1_fwd", 4 * B * P * (K + Cout) + 4 * K * Cout, 2 * B * P * K * Cout, _lib.load().smaat_pw1x1_fwd, _ptr(x), _ptr(w2d), _ptr(wlo), _ptr(scale), _ptr(shift), _ptr(out), ybs, _ptr(stats),
+    _call(f"smaat_pw1x1_fwd[K{K}_N{Cout}_P{P}]", 4 * B * P * (K + Cout) + 4 * K * Cout, 2 * B * P * K * Cout, _lib.load().smaat_pw1x1_fwd, _ptr(x), _ptr(w2d), _ptr(wlo), _ptr(scale), _ptr(shift), _ptr(out), ybs, _ptr(stats),
                                            B, K, Cout, P, int(bool(relu)), m, _stream())
     return out
 
