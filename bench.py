@@ -101,6 +101,21 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def usable_cpus():
+    """Host threads this process can really use: affinity mask, capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_port_time(n_frames, reps, threads):
     """Oracle leg (allowed to import oracle/): reference algorithm on the host cores."""
     import numpy as np
@@ -122,7 +137,7 @@ def cpu_port_time(n_frames, reps, threads):
 def run_reference(args, rank):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = usable_cpus()
     n = 4
     ts = cpu_port_time(n, args.warmup + args.steps, threads)[args.warmup:]
     sec = sum(ts)
@@ -162,14 +177,14 @@ def main():
 
     import torch.distributed as dist
     import smaat_unet_b200 as S
+    from smaat_unet_b200 import parallel as PAR
     from smaat_unet_b200.engine import InferenceSession
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    PAR.init_from_env("nccl", dev)
     S.set_pointwise_mode(args.mode)
 
     gen = torch.Generator().manual_seed(0)
@@ -184,16 +199,10 @@ def main():
     host = [torch.rand((B_PER_GPU, C_IN, SIZE, SIZE), generator=gen).pin_memory() for _ in range(2)]
 
     def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
+        PAR.barrier(dev)
 
     def reduce_max(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return PAR.reduce_max(v, dev)
 
     # ---------------- device-resident throughput ("value") ----------------
     for i in range(args.warmup):
@@ -259,7 +268,7 @@ def main():
     # ---------------- CPU baseline (oracle port), rank 0, N=1 only ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = usable_cpus()
         n = 8
         ts = cpu_port_time(n, 1, threads)
         cpu = {"value": n / ts[0], "unit": "frames/s", "cores": threads, "kind": "port",

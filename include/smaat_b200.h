@@ -77,6 +77,22 @@ int smaat_pw1x1_fwd(const float* x, const float* w, const float* w_lo,
                     float* y, int64_t y_bstride, float* stats,
                     int B, int K, int Cout, int P, int relu, int mode, void* stream);
 
+/* ---- fused DepthwiseSeparableConv: depthwise 3x3 -> pointwise 1x1 -> affine (+ReLU) in ONE kernel ----
+ * replaces DepthwiseSeparableConv.forward (models/layers.py:47-50) + eval BatchNorm2d + ReLU
+ * (parts_ds.py:25-26,34-35); the k*Cin-channel depthwise result stays on chip (CUDA-core stencil writes
+ * the tcgen05 A operand directly).  Arguments as smaat_dw3x3_fwd (input = virtual concat [x0, x1],
+ * dw_w: (k*Cin,3,3), dw_b: (k*Cin) or NULL) and smaat_pw1x1_fwd (pw_w: (Cout, k*Cin) -- the tf32 hi
+ * parts in TF32X3 mode, pw_w_lo the lo parts; scale/shift/stats/relu as there).
+ * mode: SMAAT_PW_TF32 or SMAAT_PW_TF32X3.  Returns SMAAT_E_UNSUPPORTED for shapes the fused kernel
+ * does not take (k not in {1,2}, Cout > 128, W % 4, patch waste > 35 %): callers then run
+ * smaat_dw3x3_fwd + smaat_pw1x1_fwd.  smaat_dsconv_eligible returns 1/0 for the same test. */
+int smaat_dsconv_eligible(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
+                          const float* pw_w, int H, int W, int k, int Cout);
+int smaat_dsconv_fwd(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
+                     const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_w_lo,
+                     const float* scale, const float* shift, float* y, int64_t y_bstride, float* stats,
+                     int B, int H, int W, int k, int Cout, int relu, int mode, void* stream);
+
 /* 1 if this (x, w, K, Cout, P) can take the tcgen05 path (P % 4 == 0, K % 4 == 0, 16-byte aligned
  * pointers, Cout >= 8), else 0: the caller then uses SMAAT_PW_FP32_SIMT. */
 int smaat_pw1x1_tc_eligible(const float* x, const float* w, int K, int Cout, int P);

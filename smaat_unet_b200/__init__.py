@@ -9,7 +9,7 @@ from . import _lib, ops  # noqa: F401
 from .model import SmaAt_UNet  # noqa: F401
 from .modules import (CBAM, ChannelAttention, DepthwiseSeparableConv, DoubleConvDS, DownDS, OutConv,  # noqa: F401
                       SpatialAttention, UpDS)
-from .ops import get_pointwise_mode, set_pointwise_mode  # noqa: F401
+from .ops import get_pointwise_mode, set_fused_dsconv, set_pointwise_mode  # noqa: F401
 from .patch import patch_reference  # noqa: F401
 
 __all__ = ["SmaAt_UNet", "CBAM", "ChannelAttention", "SpatialAttention", "DepthwiseSeparableConv", "DoubleConvDS",

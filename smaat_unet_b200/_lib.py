@@ -22,6 +22,8 @@ SIGNATURES = {
     "smaat_dw3x3_fwd": [_p, _i, _l, _p, _i, _l, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "smaat_pw1x1_fwd": [_p, _p, _p, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _p],
     "smaat_pw1x1_tc_eligible": [_p, _p, _i, _i, _i],
+    "smaat_dsconv_eligible": [_p, _i, _l, _p, _i, _l, _p, _i, _i, _i, _i],
+    "smaat_dsconv_fwd": [_p, _i, _l, _p, _i, _l, _p, _p, _p, _p, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "smaat_split_tf32": [_p, _p, _p, _l, _p],
     "smaat_bn_fold": [_p, _p, _p, _p, _p, _f, _p, _p, _i, _p],
     "smaat_maxpool2_fwd": [_p, _p, _l, _i, _i, _p],

@@ -6,14 +6,14 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=../libsmaat_b200.so
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O2,-Wall
        -Xptxas -v -cudart static)
-SRCS=(runtime.cu dw3x3.cu pw1x1.cu pw1x1_simt.cu pw1x1_tc.cu glue.cu cbam.cu)
+SRCS=(runtime.cu dw3x3.cu pw1x1.cu pw1x1_simt.cu pw1x1_tc.cu dsconv_fused.cu glue.cu upsample.cu cbam.cu)
 mkdir -p ../../build
 OBJS=()
 pids=()
 for s in "${SRCS[@]}"; do
   o=../../build/${s%.cu}.o
   OBJS+=("$o")
-  if [[ ! -f "$o" || "$s" -nt "$o" || common.cuh -nt "$o" || ../../include/smaat_b200.h -nt "$o" ]]; then
+  if [[ ! -f "$o" || "$s" -nt "$o" || common.cuh -nt "$o" || tc_common.cuh -nt "$o" || ../../include/smaat_b200.h -nt "$o" ]]; then
     ( "$NVCC" "${FLAGS[@]}" -c "$s" -o "$o" > "../../build/${s%.cu}.log" 2>&1 || { cat "../../build/${s%.cu}.log"; exit 1; } ) &
     pids+=($!)
   fi

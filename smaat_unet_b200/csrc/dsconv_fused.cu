@@ -1,0 +1,487 @@
+// dsconv_fused.cu -- DepthwiseSeparableConv forward as ONE kernel: depthwise 3x3 on the CUDA
+// cores feeding the pointwise 1x1 on the tensor cores, with the BN-affine/ReLU epilogue.
+//
+// Replaces DepthwiseSeparableConv.forward (reference models/layers.py:47-50: depthwise then
+// pointwise, nothing in between) + eval BatchNorm2d + ReLU (parts_ds.py:25-26,34-35).  The
+// k x -expanded depthwise result never reaches HBM: per B=32 forward the DS blocks move
+// 4*B*S^2*(Cin + Cout) bytes instead of 4*B*S^2*(Cin + 2*k*Cin + Cout) (32.7 -> 10.4 GB).
+//
+// One persistent CTA per SM; a tile is a PH x PW = 128-pixel patch of one image (M = 128 TMEM
+// lanes) and ALL Cout <= 128 output channels (N_TILE TMEM columns), so the depthwise work is done
+// exactly once.  K = k*Cin is walked in chunks of 32 depthwise channels (CC = 32/k input channels):
+//   warp 0      TMA: (PH+2) x (PW+8) x CC input halo box per chunk (OOB zero fill = padding=1; box
+//               starts at x0-4: the inner TMA coordinate must be 16-byte aligned) into an IS-deep ring;
+//               input may be the virtual concat [x0, x1] of UpDS (parts_ds.py:85)
+//   warps 6-13  two depthwise producer groups (128 threads each; each takes every other chunk, writing
+//               into a 3-stage A ring so a group never waits for its own chunk's MMAs): 3x3 stencil from the staged tile with a sliding register
+//               window, then write the result straight into the UMMA A-operand layout (MN-major tf32,
+//               128B span / 32B-atom swizzle) -- as hi and lo tf32 parts in TF32X3 mode (the split is
+//               free here: values are in registers); the weight chunks (K-major SW128, hi [+lo]) are
+//               prefetched by warp 14 into their own ring
+//   warp 1      one lane issues tcgen05.mma kind::tf32 (1 or 3 per k-step) into TMEM, commits
+//   warps 2-5   epilogue: tcgen05.ld (lane = pixel) -> scale/shift/ReLU -> coalesced NCHW stores;
+//               two TMEM accumulator stages overlap it with the next tile's MMAs
+#include "tc_common.cuh"
+
+namespace smaat {
+
+struct DsParams {
+  const float* dw_w;
+  const float* dw_b;
+  const float* scale;
+  const float* shift;
+  float* y;
+  int64_t y_bstride;
+  float* stats;
+  int C0, C1, H, W, Cout, relu, K;
+  int tiles_x, tiles_y, total_tiles, nchunks;
+};
+
+template <int N_TILE, int KPL, int PW, bool X3>
+struct DsCfg {
+  static constexpr int PH = TC_BM / PW;
+  static constexpr int BW = PW + 8, BH = PH + 2;
+  static constexpr int CC = TC_BK / KPL;                       // input channels per chunk
+  static constexpr int IN_BYTES = CC * BH * BW * 4;            // multiple of 128 for PW in {16,32}
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;            // 16 KB
+  static constexpr int B_BYTES = N_TILE * TC_BK * 4;
+  static constexpr int AST_BYTES = (X3 ? 2 : 1) * A_BYTES;     // A ring stage: hi [+ lo]
+  static constexpr int BST_BYTES = (X3 ? 2 : 1) * B_BYTES;     // B ring stage: hi [+ lo]
+  static constexpr int OFF_ALO = A_BYTES;
+  static constexpr int OFF_BLO = B_BYTES;
+  static constexpr int AS = (KPL == 1 && X3 && N_TILE > 64) ? 2 : 3;  // A ring (2 producer groups alternate over it)
+  static constexpr int BS = X3 ? (N_TILE > 64 ? 2 : 3) : 4;     // weight ring, prefetched by the TMA warp
+  static constexpr int IS_FIT = (218 * 1024 - AS * AST_BYTES - BS * BST_BYTES) / IN_BYTES;
+  static constexpr int IS = IS_FIT > 8 ? 8 : IS_FIT;           // input ring: as deep as shared memory allows
+  static constexpr int OFF_A = ((IS * IN_BYTES + 1023) / 1024) * 1024;
+  static constexpr int OFF_BR = OFF_A + AS * AST_BYTES;
+  static constexpr int OFF_BAR = OFF_BR + BS * BST_BYTES;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int AFF_N = 128;
+  static constexpr int TOTAL = OFF_BAR + BAR_BYTES + 2 * AFF_N * 4 + 1024;
+  static constexpr uint32_t B_TX = BST_BYTES;
+  static constexpr int THREADS = 64 + 128 + 256 + 32;         // + warp 14: weight-ring loader
+  static_assert(IS >= 2, "input ring");
+  static constexpr int TMEM_COLS = 2 * N_TILE;
+  static_assert(IN_BYTES % 128 == 0, "TMA destination alignment");
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+  static_assert(N_TILE <= AFF_N, "epilogue affine staging");
+};
+
+template <int N_TILE, int KPL, int PW, bool X3>
+__global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
+    dsconv_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constant__ CUtensorMap map_in1,
+                        const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
+                        const DsParams p) {
+  using L = DsCfg<N_TILE, KPL, PW, X3>;
+  constexpr int PH = L::PH, BW = L::BW, BH = L::BH, CC = L::CC, IS = L::IS, AS = L::AS, BS = L::BS;
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  unsigned char* a_base = smem + L::OFF_A;
+  unsigned char* b_base = smem + L::OFF_BR;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* in_full = bars;                       // [IS] TMA input box landed
+  uint64_t* in_empty = in_full + IS;              // [IS] producer group finished reading the box (128 arrivals)
+  uint64_t* a_full = in_empty + IS;               // [AS] A operand written (128 arrivals)
+  uint64_t* a_empty = a_full + AS;                // [AS] MMAs reading the A stage retired (commit)
+  uint64_t* b_full = a_empty + AS;                // [BS] weight chunk landed (TMA tx)
+  uint64_t* b_empty = b_full + BS;                // [BS] MMAs reading the B stage retired (commit)
+  uint64_t* tmem_full = b_empty + BS;             // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]  (128 arrivals)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* aff = reinterpret_cast<float*>(smem + L::OFF_BAR + L::BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nch = p.nchunks;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_in0);
+    tma_prefetch_desc(&map_in1);
+    tma_prefetch_desc(&map_w);
+    if (X3) tma_prefetch_desc(&map_wlo);
+    for (int s = 0; s < IS; ++s) {
+      mbar_init(&in_full[s], 1);
+      mbar_init(&in_empty[s], 128);
+    }
+    for (int s = 0; s < AS; ++s) {
+      mbar_init(&a_full[s], 128);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < BS; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, L::TMEM_COLS);
+  for (int c = threadIdx.x; c < L::AFF_N; c += blockDim.x) {
+    aff[c] = (c < p.Cout && p.scale) ? __ldg(p.scale + c) : 1.f;
+    aff[L::AFF_N + c] = (c < p.Cout && p.shift) ? __ldg(p.shift + c) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA: input halo boxes, running ahead through the IS-deep ring =====
+    if (lane == 0) {
+      uint32_t gc = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img;
+        const int t2 = tile - b * tiles_per_img;
+        const int ty = t2 / p.tiles_x, tx = t2 - ty * p.tiles_x;
+        const int x0 = tx * PW, y0 = ty * PH;
+        for (int i = 0; i < nch; ++i, ++gc) {
+          const int s = gc % IS;
+          mbar_wait(&in_empty[s], ((gc / IS) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&in_full[s], L::IN_BYTES);
+          const int cb = i * CC;
+          const CUtensorMap* m = (cb < p.C0) ? &map_in0 : &map_in1;
+          const int cc = (cb < p.C0) ? cb : cb - p.C0;
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+                  "r"(smem_u32(smem + s * L::IN_BYTES)),
+              "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(&in_full[s])), "r"(x0 - 4), "r"(y0 - 1), "r"(cc), "r"(b)
+              : "memory");
+          // pull the same chunk of this CTA's NEXT tile into L2 now: by the time it is TMA-loaded the HBM
+          // latency is already paid, so a few 15 KB boxes in flight per SM are enough to stream at HBM speed
+          const int ntile = tile + gridDim.x;
+          if (ntile < p.total_tiles) {
+            const int nb = ntile / tiles_per_img;
+            const int nt2 = ntile - nb * tiles_per_img;
+            const int nty = nt2 / p.tiles_x, ntx = nt2 - nty * p.tiles_x;
+            asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                             reinterpret_cast<uint64_t>(m)),
+                         "r"(ntx * PW - 4), "r"(nty * PH - 1), "r"(cc), "r"(nb)
+                         : "memory");
+          }
+        }
+      }
+    }
+  } else if (warp == 14) {
+    // ===== weight-ring loader: K-major SW128 chunks (hi [+lo]), decoupled from the input ring =====
+    if (lane == 0) {
+      uint32_t gc = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int i = 0; i < nch; ++i, ++gc) {
+          const int sb = gc % BS;
+          mbar_wait(&b_empty[sb], ((gc / BS) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&b_full[sb], L::B_TX);
+          tma_load_2d(b_base + sb * L::BST_BYTES, &map_w, &b_full[sb], i * TC_BK, 0);
+          if (X3) tma_load_2d(b_base + sb * L::BST_BYTES + L::OFF_BLO, &map_wlo, &b_full[sb], i * TC_BK, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(N_TILE);
+      uint32_t gc = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u;
+        mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        for (int i = 0; i < nch; ++i, ++gc) {
+          const int sa = gc % AS, sb = gc % BS;
+          mbar_wait(&a_full[sa], (gc / AS) & 1u);
+          mbar_wait(&b_full[sb], (gc / BS) & 1u);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_base + sa * L::AST_BYTES);
+          const uint32_t b_addr = smem_u32(b_base + sb * L::BST_BYTES);
+          const int kc = min(TC_BK, p.K - i * TC_BK);
+          const int nmma = (kc + 7) >> 3;
+          for (int kk = 0; kk < nmma; ++kk) {
+            const uint64_t ad = make_a_desc(a_addr + kk * 1024, TC_BK * 128);
+            const uint64_t bd = make_b_desc(b_addr + kk * 32);
+            umma_tf32(d_tmem, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            if (X3) {
+              umma_tf32(d_tmem, make_a_desc(a_addr + L::OFF_ALO + kk * 1024, TC_BK * 128), bd, idesc, 1u);
+              umma_tf32(d_tmem, ad, make_b_desc(b_addr + L::OFF_BLO + kk * 32), idesc, 1u);
+            }
+          }
+          umma_commit(&a_empty[sa]);  // each commit tracks completion of all MMAs issued so far
+          umma_commit(&b_empty[sb]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== epilogue warps 2..5 =====
+    const int q = warp & 3;
+    const float act_lo = p.relu ? 0.f : -INFINITY;
+    const int m = q * 32 + lane;  // pixel of the patch = TMEM lane
+    const int pr = m / PW, pc = m % PW;
+    const int64_t P = (int64_t)p.H * p.W;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const int b = tile / tiles_per_img;
+      const int t2 = tile - b * tiles_per_img;
+      const int ty = t2 / p.tiles_x, tx = t2 - ty * p.tiles_x;
+      const int gy = ty * PH + pr, gx = tx * PW + pc;
+      const bool pvalid = (gy < p.H) && (gx < p.W);
+      const uint32_t acc = tcount & 1u;
+      mbar_wait(&tmem_full[acc], (tcount >> 1) & 1u);
+      tc_fence_after();
+      float* ypix = p.y + (int64_t)b * p.y_bstride + (int64_t)gy * p.W + gx;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        if (c0 >= p.Cout) break;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE + (uint32_t)c0, r);
+        float scv[32], shv[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 a = *reinterpret_cast<const float4*>(aff + c0 + 4 * j4);
+          const float4 t = *reinterpret_cast<const float4*>(aff + L::AFF_N + c0 + 4 * j4);
+          scv[4 * j4] = a.x; scv[4 * j4 + 1] = a.y; scv[4 * j4 + 2] = a.z; scv[4 * j4 + 3] = a.w;
+          shv[4 * j4] = t.x; shv[4 * j4 + 1] = t.y; shv[4 * j4 + 2] = t.z; shv[4 * j4 + 3] = t.w;
+        }
+        tmem_ld_wait();
+        const int nchn = min(32, p.Cout - c0);
+        float* yp = ypix + (int64_t)c0 * P;
+        if (p.stats == nullptr && nchn == 32) {
+          if (pvalid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              *yp = fmaxf(fmaf(__uint_as_float(r[j]), scv[j], shv[j]), act_lo);
+              yp += P;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nchn) {
+              const float pre = fmaf(__uint_as_float(r[j]), scv[j], shv[j]);
+              if (p.stats) {
+                const float mv = pvalid ? pre : 0.f;
+                const float s1 = warp_sum(mv), s2 = warp_sum(mv * mv);
+                if (lane == 0) {
+                  atomicAdd(p.stats + c0 + j, s1);
+                  atomicAdd(p.stats + p.Cout + c0 + j, s2);
+                }
+              }
+              if (pvalid) yp[(int64_t)j * P] = fmaxf(pre, act_lo);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  } else {
+    // ===== depthwise producer groups: warps 6-9 (group 0), 10-13 (group 1) =====
+    const int g = (warp - 6) >> 2;
+    const int t = threadIdx.x - 192 - 128 * g;  // 0..127
+    const int Cin = p.C0 + p.C1;
+    uint32_t gc = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int i = 0; i < nch; ++i, ++gc) {
+        if ((int)(gc & 1u) != g) continue;
+        const int s = gc % IS;
+        mbar_wait(&in_full[s], (gc / IS) & 1u);
+        const int sa = gc % AS;
+        mbar_wait(&a_empty[sa], ((gc / AS) & 1u) ^ 1u);  // MMAs that read this A stage 3 chunks ago retired
+        unsigned char* my_op = a_base + sa * L::AST_BYTES;
+        const float* in_stage = reinterpret_cast<const float*>(smem + s * L::IN_BYTES);
+#pragma unroll 1
+        for (int task = t; task < CC * 8; task += 128) {
+          const int ci = task >> 3, strip = task & 7;
+          const int qc = strip % (PW / 4), rg = strip / (PW / 4);
+          const int c0 = qc << 2, r0 = rg << 2;
+          const int gch = i * CC + ci;  // global input channel of this task
+          float wr[KPL][9], br[KPL];
+          const bool chv = gch < Cin;
+#pragma unroll
+          for (int kk = 0; kk < KPL; ++kk) {
+            const int gk = gch * KPL + kk;
+#pragma unroll
+            for (int w9 = 0; w9 < 9; ++w9) wr[kk][w9] = chv ? __ldg(p.dw_w + (int64_t)gk * 9 + w9) : 0.f;
+            br[kk] = (chv && p.dw_b) ? __ldg(p.dw_b + gk) : 0.f;
+          }
+          // smem column of patch column c (dx = -1..1) is c + 4 + dx: the 4 outputs read cols c0+3 .. c0+8
+          const float* trow = in_stage + (ci * BH + r0) * BW + c0 + 3;
+          float win[3][6];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(trow + r * BW + 1);
+            win[r][0] = trow[r * BW]; win[r][1] = a.x; win[r][2] = a.y; win[r][3] = a.z; win[r][4] = a.w; win[r][5] = trow[r * BW + 5];
+          }
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            {
+              const float4 a = *reinterpret_cast<const float4*>(trow + (rr + 2) * BW + 1);
+              float* wl = win[(rr + 2) % 3];
+              wl[0] = trow[(rr + 2) * BW]; wl[1] = a.x; wl[2] = a.y; wl[3] = a.z; wl[4] = a.w; wl[5] = trow[(rr + 2) * BW + 5];
+            }
+            const float* w0 = win[rr % 3];
+            const float* w1 = win[(rr + 1) % 3];
+            const float* w2 = win[(rr + 2) % 3];
+            const int m = (r0 + rr) * PW + c0;
+#pragma unroll
+            for (int kk = 0; kk < KPL; ++kk) {
+              float o4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float a = br[kk];
+                a = fmaf(wr[kk][0], w0[j], a); a = fmaf(wr[kk][1], w0[j + 1], a); a = fmaf(wr[kk][2], w0[j + 2], a);
+                a = fmaf(wr[kk][3], w1[j], a); a = fmaf(wr[kk][4], w1[j + 1], a); a = fmaf(wr[kk][5], w1[j + 2], a);
+                a = fmaf(wr[kk][6], w2[j], a); a = fmaf(wr[kk][7], w2[j + 1], a); a = fmaf(wr[kk][8], w2[j + 2], a);
+                o4[j] = a;
+              }
+              const uint32_t off = a_tile_offset(ci * KPL + kk, m);
+              if (X3) {
+                const float4 h = make_float4(tf32_hi(o4[0]), tf32_hi(o4[1]), tf32_hi(o4[2]), tf32_hi(o4[3]));
+                *reinterpret_cast<float4*>(my_op + off) = h;
+                *reinterpret_cast<float4*>(my_op + L::OFF_ALO + off) = make_float4(o4[0] - h.x, o4[1] - h.y, o4[2] - h.z, o4[3] - h.w);
+              } else {
+                *reinterpret_cast<float4*>(my_op + off) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        mbar_arrive(&a_full[sa]);
+        mbar_arrive(&in_empty[s]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
+  }
+}
+
+template <int N_TILE, int KPL, int PW, bool X3>
+static int launch_ds(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const CUtensorMap& mwl, DsParams p,
+                     int B, cudaStream_t st) {
+  using L = DsCfg<N_TILE, KPL, PW, X3>;
+  auto kern = dsconv_fused_kernel<N_TILE, KPL, PW, X3>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "dsconv: smem attribute (%d B): %s", L::TOTAL, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  p.tiles_x = ceil_div(p.W, PW);
+  p.tiles_y = ceil_div(p.H, L::PH);
+  const int64_t total = (int64_t)B * p.tiles_x * p.tiles_y;
+  SMAAT_REQUIRE(total < (1ll << 31), "dsconv: too many tiles");
+  p.total_tiles = (int)total;
+  p.nchunks = ceil_div(p.C0 + p.C1, L::CC);
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  kern<<<grid, L::THREADS, L::TOTAL, st>>>(m0, m1, mw, mwl, p);
+  SMAAT_LAUNCH_CHECK("smaat_dsconv_fwd");
+  return SMAAT_OK;
+}
+
+// patch width: 32 (PH = 4) or 16 (PH = 8), whichever wastes fewer MMA lanes; 0 = not worth fusing
+static int pick_pw(int H, int W) {
+  double best = 1e9;
+  int pw = 0;
+  const int cand[2] = {32, 16};
+  for (int i = 0; i < 2; ++i) {
+    const int c = cand[i], ph = TC_BM / c;
+    const double waste = ((double)ceil_div(W, c) * c / W) * ((double)ceil_div(H, ph) * ph / H);
+    if (waste < best - 1e-9) {
+      best = waste;
+      pw = c;
+    }
+  }
+  return best <= 1.35 ? pw : 0;
+}
+
+static bool ds_eligible(const float* x0, int C0, int64_t bs0, const float* x1, int C1, int64_t bs1, const float* pw_w,
+                        const float* pw_w_lo, int H, int W, int k, int Cout) {
+  if (k != 1 && k != 2) return false;
+  if (Cout > 128 || Cout < 8) return false;
+  if (W % 4 != 0 || !aligned16(x0) || bs0 % 4 != 0) return false;
+  if (C1 > 0 && (!aligned16(x1) || bs1 % 4 != 0 || C0 % (TC_BK / k) != 0)) return false;
+  const int K = k * (C0 + C1);
+  if (K % 4 != 0 || !aligned16(pw_w) || (pw_w_lo && !aligned16(pw_w_lo))) return false;
+  return pick_pw(H, W) != 0;
+}
+
+}  // namespace smaat
+
+using namespace smaat;
+
+extern "C" int smaat_dsconv_eligible(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
+                                     const float* pw_w, int H, int W, int k, int Cout) {
+  return ds_eligible(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, nullptr, H, W, k, Cout) ? 1 : 0;
+}
+
+extern "C" int smaat_dsconv_fwd(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
+                                const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_w_lo,
+                                const float* scale, const float* shift, float* y, int64_t y_bstride, float* stats, int B, int H,
+                                int W, int k, int Cout, int relu, int mode, void* stream) {
+  SMAAT_REQUIRE(x0 && dw_w && pw_w && y, "dsconv: null pointer");
+  SMAAT_REQUIRE(B > 0 && C0 > 0 && C1 >= 0 && H > 0 && W > 0 && Cout > 0, "dsconv: bad shape");
+  SMAAT_REQUIRE(C1 == 0 || x1, "dsconv: C1=%d but x1 is null", C1);
+  SMAAT_REQUIRE(mode == SMAAT_PW_TF32 || mode == SMAAT_PW_TF32X3, "dsconv: mode must be SMAAT_PW_TF32 or SMAAT_PW_TF32X3");
+  SMAAT_REQUIRE(mode != SMAAT_PW_TF32X3 || pw_w_lo, "dsconv: TF32X3 needs pw_w_lo (see smaat_split_tf32)");
+  SMAAT_REQUIRE(y_bstride >= (int64_t)Cout * H * W, "dsconv: y batch stride too small");
+  if (!ds_eligible(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, pw_w_lo, H, W, k, Cout))
+    return fail(SMAAT_E_UNSUPPORTED, "dsconv: shape not taken by the fused kernel (k=%d Cout=%d H=%d W=%d); use dw3x3 + pw1x1", k,
+                Cout, H, W);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pw = pick_pw(H, W);
+  const int ph = TC_BM / pw;
+  const int n_tile = Cout > 64 ? 128 : 64;
+  const int cc = TC_BK / k;
+  const bool x3 = mode == SMAAT_PW_TF32X3;
+  const int K = k * (C0 + C1);
+
+  CUtensorMap m0, m1, mw, mwl;
+  const uint32_t box[4] = {(uint32_t)(pw + 8), (uint32_t)(ph + 2), (uint32_t)cc, 1u};
+  {
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C0, (uint64_t)B};
+    const uint64_t str[4] = {0, (uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)x0_bstride * 4};
+    int r = make_tmap_f32(&m0, x0, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, "dsconv(x0)");
+    if (r) return r;
+    m1 = m0;
+  }
+  if (C1 > 0) {
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C1, (uint64_t)B};
+    const uint64_t str[4] = {0, (uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)x1_bstride * 4};
+    int r = make_tmap_f32(&m1, x1, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, "dsconv(x1)");
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)Cout};
+    const uint64_t str[2] = {0, (uint64_t)K * 4};
+    const uint32_t wbox[2] = {(uint32_t)TC_BK, (uint32_t)n_tile};
+    int r = make_tmap_f32(&mw, pw_w, 2, dims, str, wbox, CU_TENSOR_MAP_SWIZZLE_128B, "dsconv(w)");
+    if (r) return r;
+    mwl = mw;
+    if (x3) {
+      r = make_tmap_f32(&mwl, pw_w_lo, 2, dims, str, wbox, CU_TENSOR_MAP_SWIZZLE_128B, "dsconv(w_lo)");
+      if (r) return r;
+    }
+  }
+  DsParams p;
+  p.dw_w = dw_w; p.dw_b = dw_b; p.scale = scale; p.shift = shift; p.y = y; p.y_bstride = y_bstride; p.stats = stats;
+  p.C0 = C0; p.C1 = C1; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu; p.K = K;
+  p.tiles_x = p.tiles_y = p.total_tiles = p.nchunks = 0;
+
+#define DS_DISPATCH(NT, KP, PWv)                                                   \
+  return x3 ? launch_ds<NT, KP, PWv, true>(m0, m1, mw, mwl, p, B, st)              \
+            : launch_ds<NT, KP, PWv, false>(m0, m1, mw, mwl, p, B, st)
+  if (n_tile == 64) {
+    if (k == 2) { if (pw == 32) { DS_DISPATCH(64, 2, 32); } else { DS_DISPATCH(64, 2, 16); } }
+    else        { if (pw == 32) { DS_DISPATCH(64, 1, 32); } else { DS_DISPATCH(64, 1, 16); } }
+  } else {
+    if (k == 2) { if (pw == 32) { DS_DISPATCH(128, 2, 32); } else { DS_DISPATCH(128, 2, 16); } }
+    else        { if (pw == 32) { DS_DISPATCH(128, 1, 32); } else { DS_DISPATCH(128, 1, 16); } }
+  }
+#undef DS_DISPATCH
+}

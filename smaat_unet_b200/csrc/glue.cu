@@ -1,5 +1,5 @@
 // glue.cu -- the memory-bound glue between the DS-conv blocks: BN folding, MaxPool2d(2),
-// bilinear x2 (align_corners) + pad, OutConv, tf32 weight split.  All are streaming kernels
+// OutConv, tf32 weight split (bilinear x2 + pad lives in upsample.cu).  All are streaming kernels
 // (no reuse beyond what L1/L2 give for free); coalesced 128-bit accesses where alignment allows.
 #include "common.cuh"
 
@@ -51,55 +51,6 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__
       const float* s = r0 + 2 * q;
       y[(n * Ho + oy) * (int64_t)Wo + q] = fmaxf(fmaxf(__ldg(s), __ldg(s + 1)), fmaxf(__ldg(s + W), __ldg(s + W + 1)));
     }
-  }
-}
-
-// ---- bilinear x2 (align_corners=True) + zero pad ------------------------------------------------
-// grid = (row-quads of one plane, C, B): 32-bit index math only; one thread -> 4 consecutive output
-// pixels of one row (one 128-bit store); the 2 source rows / <= 4 source columns it needs come from
-// a 4x smaller plane that stays in L1/L2.  Index math follows torch's area_pixel_compute_source_index
-// for align_corners=True: src = dst * (in-1)/(out-1).
-template <bool VEC>
-__global__ void __launch_bounds__(256) upsample2x_pad_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                             int64_t y_bstride, int C, int H, int W, int Ho, int Wo,
-                                                             int pad_t, int pad_l, float ry, float rx) {
-  const int wq = (Wo + 3) >> 2;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Ho * wq) return;
-  const int oy = idx / wq;
-  const int ox0 = (idx - oy * wq) << 2;
-  const int c = blockIdx.y, b = blockIdx.z;
-  const float* src = x + ((int64_t)b * C + c) * H * W;
-  float* dst = y + (int64_t)b * y_bstride + ((int64_t)c * Ho + oy) * Wo + ox0;
-  float o[4] = {0.f, 0.f, 0.f, 0.f};
-  const int uy = oy - pad_t;
-  if (uy >= 0 && uy < 2 * H) {
-    const float sy = ry * uy;
-    int y0 = min((int)sy, H - 1);
-    const int y1 = min(y0 + 1, H - 1);
-    const float ly = sy - y0;
-    const float* r0 = src + y0 * W;
-    const float* r1 = src + y1 * W;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int ux = ox0 + j - pad_l;
-      if (ux >= 0 && ux < 2 * W) {
-        const float sx = rx * ux;
-        const int x0 = min((int)sx, W - 1);
-        const int x1 = min(x0 + 1, W - 1);
-        const float lx = sx - x0;
-        // same association as torch's upsample_bilinear2d: w_y0*(w_x0*v00 + w_x1*v01) + w_y1*(...)
-        o[j] = (1.f - ly) * ((1.f - lx) * __ldg(r0 + x0) + lx * __ldg(r0 + x1)) +
-               ly * ((1.f - lx) * __ldg(r1 + x0) + lx * __ldg(r1 + x1));
-      }
-    }
-  }
-  if (VEC) {
-    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (ox0 + j < Wo) dst[j] = o[j];
   }
 }
 
@@ -194,26 +145,6 @@ extern "C" int smaat_maxpool2_fwd(const float* x, float* y, int64_t N, int H, in
   else
     maxpool2_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, Ho, Wo);
   SMAAT_LAUNCH_CHECK("smaat_maxpool2_fwd");
-  return SMAAT_OK;
-}
-
-extern "C" int smaat_upsample2x_pad_fwd(const float* x, float* y, int64_t y_bstride, int B, int C, int H, int W, int Ho, int Wo,
-                                        void* stream) {
-  SMAAT_REQUIRE(x && y && B > 0 && C > 0 && H > 0 && W > 0, "upsample2x: bad arguments");
-  SMAAT_REQUIRE(Ho >= 2 * H && Wo >= 2 * W, "upsample2x: target %dx%d smaller than 2x source %dx%d (negative pad = crop unsupported)",
-                Ho, Wo, H, W);
-  SMAAT_REQUIRE(y_bstride >= (int64_t)C * Ho * Wo, "upsample2x: y batch stride too small");
-  const int pad_t = (Ho - 2 * H) / 2, pad_l = (Wo - 2 * W) / 2;
-  const float ry = (2 * H > 1) ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
-  const float rx = (2 * W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
-  SMAAT_REQUIRE(C <= 65535 && B <= 65535, "upsample2x: C/B too large for grid.y/z");
-  const bool vec = (Wo % 4 == 0) && aligned16(y) && (y_bstride % 4 == 0);
-  dim3 grid(ceil_div(Ho * ceil_div(Wo, 4), 256), C, B);
-  if (vec)
-    upsample2x_pad_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx);
-  else
-    upsample2x_pad_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx);
-  SMAAT_LAUNCH_CHECK("smaat_upsample2x_pad_fwd");
   return SMAAT_OK;
 }
 

@@ -63,12 +63,18 @@ class DepthwiseSeparableConv(nn.Module):
     def run(self, x, x1=None, scale=None, shift=None, relu=False, in_scale=None, in_shift=None, stats=None):
         """dw -> pw with the pw epilogue y = act(scale * acc + shift).  scale/shift None => (1, pointwise.bias)."""
         self._check()
-        d = ops.dw3x3(x, self.depthwise.weight.detach(), self.depthwise.bias.detach() if self.depthwise.bias is not None else None,
-                      self.kernels_per_layer, x1=x1, in_scale=in_scale, in_shift=in_shift)
+        dw_b = self.depthwise.bias.detach() if self.depthwise.bias is not None else None
         if shift is None:
             shift = self.pointwise.bias.detach() if self.pointwise.bias is not None else None
         mode = ops.get_pointwise_mode()
         split = self.pw_split() if mode == "tf32x3" else None
+        if in_scale is None:
+            # one kernel: the k*Cin-channel depthwise result never reaches HBM (where the shape allows)
+            y = ops.dsconv(x, self.depthwise.weight.detach(), dw_b, self.kernels_per_layer, self.pointwise.weight.detach(),
+                           scale, shift, relu, x1=x1, mode=mode, w_split=split, stats=stats)
+            if y is not None:
+                return y
+        d = ops.dw3x3(x, self.depthwise.weight.detach(), dw_b, self.kernels_per_layer, x1=x1, in_scale=in_scale, in_shift=in_shift)
         return ops.pw1x1(d, self.pointwise.weight.detach(), scale, shift, relu, mode=mode, w_split=split, stats=stats)
 
     def forward(self, x):

@@ -168,6 +168,45 @@ def pw1x1(x, weight, scale, shift, relu, mode=None, w_split=None, stats=None, ou
     return out
 
 
+_fuse_ds = os.environ.get("SMAAT_FUSE_DS", "1") != "0"
+
+
+def set_fused_dsconv(enabled: bool) -> None:
+    """Enable/disable the fused depthwise->pointwise kernel (default on; off = dw3x3 + pw1x1 kernels)."""
+    global _fuse_ds
+    _fuse_ds = bool(enabled)
+
+
+def dsconv(x, dw_weight, dw_bias, k, pw_weight, scale, shift, relu, x1=None, mode=None, w_split=None, stats=None):
+    """Fused DepthwiseSeparableConv (layers.py:47-50) + affine (+ReLU); returns None when the fused kernel
+    does not take this shape/mode (caller then runs dw3x3 + pw1x1)."""
+    mode = mode or _pw_mode
+    if not _fuse_ds or PW_MODES[mode] == 0:
+        return None
+    x, bs0 = _nchw_bstride(x, "x")
+    B, C0, H, W = x.shape
+    C1, bs1 = 0, 0
+    if x1 is not None:
+        x1, bs1 = _nchw_bstride(x1, "x1")
+        C1 = x1.shape[1]
+    w2d = _dense(pw_weight, "pointwise.weight").view(pw_weight.shape[0], -1)
+    Cout, K = w2d.shape
+    assert K == k * (C0 + C1), f"pointwise weight {tuple(pw_weight.shape)} does not match k*Cin={k * (C0 + C1)}"
+    lib = _lib.load()
+    if not lib.smaat_dsconv_eligible(_ptr(x), C0, bs0, _ptr(x1), C1, bs1, _ptr(w2d), H, W, k, Cout):
+        return None
+    wlo = None
+    if PW_MODES[mode] == 2:
+        w2d, wlo = w_split if w_split is not None else split_tf32(w2d)
+    dw_w = _dense(dw_weight, "depthwise.weight")
+    y = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.float32)
+    Cin = C0 + C1
+    _call(f"smaat_dsconv_fwd[C{Cin}_N{Cout}_S{H}]", 4 * B * H * W * (Cin + Cout) + 4 * K * Cout, 2 * B * H * W * K * (Cout + 9),
+          lib.smaat_dsconv_fwd, _ptr(x), C0, bs0, _ptr(x1), C1, bs1, _ptr(dw_w), _ptr(dw_bias), _ptr(w2d), _ptr(wlo), _ptr(scale),
+          _ptr(shift), _ptr(y), Cout * H * W, _ptr(stats), B, H, W, k, Cout, int(bool(relu)), PW_MODES[mode], _stream())
+    return y
+
+
 def bn_fold(gamma, beta, running_mean, running_var, conv_bias, eps):
     """Eval BatchNorm2d -> (scale, shift) for the pw epilogue (parts_ds.py:25,34)."""
     Cn = gamma.numel()

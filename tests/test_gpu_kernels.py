@@ -190,3 +190,54 @@ def test_cbam_gate(ks):
     sa, raw = ops.cbam_gate(dev(pooled), dev(w), dev(aff), want_raw=True)
     assert_close(raw, a, 1e-5, "gate conv")
     assert_close(sa, O.sigmoid(a * 1.3 - 0.2), 1e-5, "gate sigmoid")
+
+
+# ------------------------------------------------------------------------------ fused depthwise -> pointwise
+DS_CASES = [
+    # B, C0, C1, H, W, k, Cout
+    (2, 12, 0, 32, 32, 2, 64),     # inc.0 class: Cin < chunk (zero-filled channels), single chunk
+    (1, 64, 0, 32, 64, 2, 64),     # K = 128, 32-wide patches
+    (1, 64, 0, 48, 48, 2, 128),    # 16-wide patches (48 % 32 != 0), N_TILE 128
+    (1, 16, 16, 16, 32, 2, 32),    # virtual concat, Cout < N_TILE
+    (2, 32, 0, 24, 32, 1, 48),     # k = 1 (32 input channels per chunk), ragged channel tail
+    (1, 8, 0, 36, 52, 2, 16),      # ragged patches in x and y
+    (1, 128, 128, 16, 16, 2, 64),  # K = 512: many chunks, both producer groups, concat boundary mid-loop
+    (3, 24, 0, 8, 96, 2, 40),      # odd chunk count (3 per tile) -> groups alternate across tiles
+]
+
+
+@pytest.mark.parametrize("mode", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("case", DS_CASES)
+def test_dsconv_fused_matches_oracle(case, mode):
+    B, C0, C1, H, W, k, Cout = case
+    C = C0 + C1
+    x = rnd(B, C, H, W)
+    dw_w, dw_b = rnd(k * C, 1, 3, 3), rnd(k * C)
+    pw_w = rnd(Cout, k * C, 1, 1, lo=-0.2, hi=0.2)
+    scale, shift = rnd(Cout, lo=0.5, hi=1.5), rnd(Cout)
+    d = O.depthwise3x3(x.astype(np.float64), dw_w, dw_b, k)
+    acc = O.pointwise1x1(d, pw_w, None)
+    ref = np.maximum(acc * scale[None, :, None, None] + shift[None, :, None, None], 0)
+    x0 = dev(x[:, :C0])
+    x1 = dev(x[:, C0:]) if C1 else None
+    y = ops.dsconv(x0, dev(dw_w), dev(dw_b), k, dev(pw_w), dev(scale), dev(shift), True, x1=x1, mode=mode)
+    assert y is not None, f"fused kernel refused an eligible shape {case}"
+    torch.cuda.synchronize()
+    assert_close(y, ref, PW_TOL[mode], f"dsconv {mode} {case}")
+    # no bias / no affine / no relu + statistics
+    stats = torch.zeros(2 * Cout, device="cuda")
+    y2 = ops.dsconv(x0, dev(dw_w), None, k, dev(pw_w), None, None, False, x1=x1, mode=mode, stats=stats)
+    pre = O.pointwise1x1(O.depthwise3x3(x.astype(np.float64), dw_w, None, k), pw_w, None)
+    assert_close(y2, pre, PW_TOL[mode], f"dsconv plain {mode} {case}")
+    assert_close(stats[:Cout], pre.sum(axis=(0, 2, 3)), 2e-3 if mode == "tf32" else 1e-4, "dsconv channel sums")
+
+
+def test_dsconv_ineligible_shapes_fall_back():
+    # Cout > 128 / tiny planes are not fused: ops.dsconv says so and the module path still gives the right answer
+    assert ops.dsconv(dev(rnd(1, 16, 8, 8)), dev(rnd(32, 1, 3, 3)), None, 2, dev(rnd(256, 32, 1, 1)), None, None, False) is None
+    m = S.DepthwiseSeparableConv(16, 256, 3, padding=1, kernels_per_layer=2).cuda().eval()
+    x = rnd(1, 16, 18, 18)
+    sd = {k_: v.detach().cpu().numpy() for k_, v in m.state_dict().items()}
+    ref = O.ds_conv(x.astype(np.float64), {"m." + k_: v for k_, v in sd.items()}, "m", 2)
+    with torch.no_grad():
+        assert_close(m(dev(x)), ref, PW_TOL["tf32x3"], "unfused fallback")
