@@ -70,11 +70,11 @@ int smaat_dw3x3_fwd(const float* x0, int C0, int64_t x0_bstride,
  *   y: (B, Cout, P) with batch stride y_bstride elements.
  * w_lo: (Cout, K) low parts for SMAAT_PW_TF32X3 (w must then hold the tf32-truncated
  *   high parts, see smaat_split_tf32); NULL otherwise.
- * stats: NULL, or (2*Cout) fp32 zero-initialised accumulators receiving per-channel
+ * stats: NULL, or (2*Cout) fp64 zero-initialised accumulators receiving per-channel
  *   sum and sum of squares of the PRE-activation value scale*acc+shift (train-mode BN). */
 int smaat_pw1x1_fwd(const float* x, const float* w, const float* w_lo,
                     const float* scale, const float* shift,
-                    float* y, int64_t y_bstride, float* stats,
+                    float* y, int64_t y_bstride, double* stats,
                     int B, int K, int Cout, int P, int relu, int mode, void* stream);
 
 /* ---- fused DepthwiseSeparableConv: depthwise 3x3 -> pointwise 1x1 -> affine (+ReLU) in ONE kernel ----
@@ -90,7 +90,7 @@ int smaat_dsconv_eligible(const float* x0, int C0, int64_t x0_bstride, const flo
                           const float* pw_w, int H, int W, int k, int Cout);
 int smaat_dsconv_fwd(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
                      const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_w_lo,
-                     const float* scale, const float* shift, float* y, int64_t y_bstride, float* stats,
+                     const float* scale, const float* shift, float* y, int64_t y_bstride, double* stats,
                      int B, int H, int W, int k, int Cout, int relu, int mode, void* stream);
 
 /* 1 if this (x, w, K, Cout, P) can take the tcgen05 path (P % 4 == 0, K % 4 == 0, 16-byte aligned
@@ -105,6 +105,22 @@ int smaat_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* st
  *   shift = beta + (conv_bias - rm) * scale        (conv_bias may be NULL) */
 int smaat_bn_fold(const float* gamma, const float* beta, const float* rm, const float* rv,
                   const float* conv_bias, float eps, float* scale, float* shift, int C, void* stream);
+
+/* ---- train-mode BatchNorm2d (parts_ds.py:25,34; layers.py:120 in .train()) ----------------------
+ * The producing kernel accumulates per-channel sum / sum of squares in fp64 (`stats`, 2*C doubles,
+ * zero-initialised by the caller); smaat_channel_stats does the same for an existing tensor
+ * x: (B, C, P) (SpatialAttention's 1-channel BN).
+ * bn_finalize: mean = s1/n, var = s2/n - mean^2 (biased), scale = gamma/sqrt(var+eps),
+ *   shift = beta - mean*scale; writes mean / inv-std for the backward pass (may be NULL) and updates
+ *   running_mean <- (1-m) rm + m mean, running_var <- (1-m) rv + m var*n/(n-1)  (may be NULL).
+ * affine_act: y[b,c,p] = act(scale[c]*x[b,c,p] + shift[c]), act 0 = none, 1 = ReLU, 2 = sigmoid
+ *   (scale NULL = 1, shift NULL = 0). */
+int smaat_channel_stats(const float* x, double* stats, int B, int C, int P, void* stream);
+int smaat_bn_finalize(const double* stats, double count, const float* gamma, const float* beta, float eps, float momentum,
+                      float* running_mean, float* running_var, float* scale, float* shift,
+                      float* mean_out, float* invstd_out, int C, void* stream);
+int smaat_affine_act_fwd(const float* x, const float* scale, const float* shift, float* y,
+                         int B, int C, int P, int act, void* stream);
 
 /* ---- nn.MaxPool2d(2) (parts_ds.py:48): stride 2, floor ---------------------------------
  * x: (N, H, W) planes -> y: (N, H/2, W/2) */
@@ -139,6 +155,52 @@ int smaat_cbam_scale_fwd(const float* x, const float* sc, const float* sa, float
 /* ---- OutConv (models/unet_parts.py:67-73): 1x1 conv Cin -> ncls (small), bias, no activation */
 int smaat_outconv_fwd(const float* x, const float* w, const float* bias, float* y,
                       int B, int Cin, int ncls, int P, void* stream);
+
+/* ======================================= backward (training step) =======================================
+ * Gradients of the same path (BASELINE configs[2]); notation: z = pre-BatchNorm activation,
+ * a = act(scale*z+shift), dA = dL/da masked by the activation (act: 0 none, 1 ReLU recomputed from z).
+ * Accumulating outputs (dW, db, dgamma, dbeta, d_sc, stats-like sums) are += : the caller zero-initialises.
+ *
+ * BatchNorm(+ReLU) backward = reduce -> coeffs -> apply:
+ *   reduce: sums[c] += sum dA, sums[C+c] += sum dA*z                       (fp64)
+ *   coeffs: dgamma += invstd*(S2 - mean*S1), dbeta += S1; per-channel a,b,cc with dz = a*dA + b*z + cc
+ *           (train: batch-statistics terms; eval (train=0): dz = gamma*invstd*dA)
+ *   apply : dz[b,c,p] = a[c]*dA + b[c]*z + cc[c] */
+int smaat_bn_act_bwd_reduce(const float* dy, const float* z, const float* scale, const float* shift, double* sums,
+                            int B, int C, int P, int act, void* stream);
+int smaat_bn_bwd_coeffs(const double* sums, double count, const float* gamma, const float* mean, const float* invstd, int train,
+                        float* a, float* b, float* cc, float* dgamma, float* dbeta, int C, void* stream);
+int smaat_bn_act_bwd_apply(const float* dy, const float* z, const float* scale, const float* shift,
+                           const float* a, const float* b, const float* cc, float* dz, int B, int C, int P, int act, void* stream);
+
+/* depthwise 3x3 backward: input gradient (split over the virtual concat x0|x1) and weight/bias gradient;
+ * in_scale/in_shift: the forward's on-load BN+ReLU prologue (input of the conv was relu(in_scale*x+in_shift)). */
+int smaat_dw3x3_bwd_input(const float* dd, const float* w, float* dx0, int C0, int64_t dx0_bstride,
+                          float* dx1, int C1, int64_t dx1_bstride, int B, int H, int W, int k, void* stream);
+int smaat_dw3x3_bwd_weight(const float* dd, const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
+                           const float* in_scale, const float* in_shift, float* dw, float* db,
+                           int B, int H, int W, int k, void* stream);
+
+/* pointwise 1x1: dW[o][c] += sum_{b,p} dz[b,o,p]*d[b,c,p], db[o] += sum dz.  (The input gradient is
+ * smaat_pw1x1_fwd(dz, W^T): use smaat_transpose for W^T.) */
+int smaat_pw1x1_bwd_weight(const float* dz, const float* d, float* dW, float* db, int B, int K, int Cout, int P, void* stream);
+int smaat_transpose(const float* src, float* dst, int rows, int cols, void* stream);
+
+int smaat_maxpool2_bwd(const float* x, const float* dy, float* dx, int64_t N, int H, int W, void* stream);
+int smaat_upsample2x_pad_bwd(const float* dy, int64_t dy_bstride, float* dx, int B, int C, int H, int W, int Ho, int Wo, void* stream);
+int smaat_outconv_bwd(const float* dy, const float* x, const float* w, float* dx, float* dW, float* db,
+                      int B, int Cin, int ncls, int P, void* stream);
+
+/* CBAM backward (see cbam_bwd.cu for the chain): */
+int smaat_cbam_bwd_gate_in(const float* g, const float* x, const float* sc, const float* sa, float* dpre, int B, int C, int P, void* stream);
+int smaat_cbam_gate_bwd(const float* draw, const float* pooled, const float* wsp, float* dpooled, float* dW,
+                        int B, int H, int W, int ks, void* stream);
+int smaat_cbam_bwd_main(const float* g, const float* x, const float* sc, const float* sa, const float* dpooled,
+                        float* dx, float* dsc, int B, int C, int P, void* stream);
+int smaat_cbam_mlp_bwd(const float* avg, const float* mx, const float* w1, const float* b1, const float* w2, const float* sc,
+                       const float* dsc, float* dw1, float* db1, float* dw2, float* db2, float* davg, float* dmx,
+                       int B, int C, int hidden, void* stream);
+int smaat_cbam_pool_bwd(const float* x, const float* davg, const float* dmx, float* dx, int64_t N, int P, void* stream);
 
 #ifdef __cplusplus
 }

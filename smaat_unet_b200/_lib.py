@@ -26,6 +26,9 @@ SIGNATURES = {
     "smaat_dsconv_fwd": [_p, _i, _l, _p, _i, _l, _p, _p, _p, _p, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "smaat_split_tf32": [_p, _p, _p, _l, _p],
     "smaat_bn_fold": [_p, _p, _p, _p, _p, _f, _p, _p, _i, _p],
+    "smaat_channel_stats": [_p, _p, _i, _i, _i, _p],
+    "smaat_bn_finalize": [_p, C.c_double, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _i, _p],
+    "smaat_affine_act_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "smaat_maxpool2_fwd": [_p, _p, _l, _i, _i, _p],
     "smaat_upsample2x_pad_fwd": [_p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
     "smaat_cbam_pool_fwd": [_p, _p, _p, _l, _i, _p],
@@ -34,6 +37,22 @@ SIGNATURES = {
     "smaat_cbam_gate_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "smaat_cbam_scale_fwd": [_p, _p, _p, _p, _l, _i, _i, _i, _p],
     "smaat_outconv_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    # ---- backward
+    "smaat_bn_act_bwd_reduce": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "smaat_bn_bwd_coeffs": [_p, C.c_double, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p],
+    "smaat_bn_act_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "smaat_dw3x3_bwd_input": [_p, _p, _p, _i, _l, _p, _i, _l, _i, _i, _i, _i, _p],
+    "smaat_dw3x3_bwd_weight": [_p, _p, _i, _l, _p, _i, _l, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "smaat_pw1x1_bwd_weight": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "smaat_transpose": [_p, _p, _i, _i, _p],
+    "smaat_maxpool2_bwd": [_p, _p, _p, _l, _i, _i, _p],
+    "smaat_upsample2x_pad_bwd": [_p, _l, _p, _i, _i, _i, _i, _i, _i, _p],
+    "smaat_outconv_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "smaat_cbam_bwd_gate_in": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "smaat_cbam_gate_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "smaat_cbam_bwd_main": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "smaat_cbam_mlp_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "smaat_cbam_pool_bwd": [_p, _p, _p, _p, _l, _i, _p],
 }
 _SPECIAL = {
     "smaat_abi_version": ([], _i),

@@ -1,0 +1,109 @@
+"""torch.autograd.Function wrappers: one node per hot-path block, forward and backward both made of
+libsmaat_b200.so kernels (functional.py).  They make the drop-in modules differentiable so the
+reference's training loops (`loss.backward()` in train_SmaAtUNet.py:55, Lightning's automatic
+optimisation over UNetBase.training_step, regression_lightning.py:67-77) run unchanged.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import functional as Fn
+from . import ops
+
+
+class DoubleConvDSFn(torch.autograd.Function):
+    """(DS conv => BN => ReLU) * 2 over the virtual concat [x, x1]."""
+
+    @staticmethod
+    def params(mod):
+        ds0, bn0, ds1, bn1 = mod.double_conv[0], mod.double_conv[1], mod.double_conv[3], mod.double_conv[4]
+        out = []
+        for ds, bn in ((ds0, bn0), (ds1, bn1)):
+            for p in (ds.depthwise.weight, ds.depthwise.bias, ds.pointwise.weight, ds.pointwise.bias, bn.weight, bn.bias):
+                if p is None:
+                    raise NotImplementedError("DoubleConvDS without conv bias / BN affine parameters is not supported in the autograd path")
+                out.append(p)
+        return out
+
+    @staticmethod
+    def run(mod, x, x1=None):
+        return DoubleConvDSFn.apply(mod, x, x1, *DoubleConvDSFn.params(mod))
+
+    @staticmethod
+    def forward(ctx, mod, x, x1, *params):
+        x = ops._dense(x, "x")
+        x1 = ops._dense(x1, "x1") if x1 is not None else None
+        out, saved = Fn.double_conv_fwd(mod, x, x1)
+        ctx.mod, ctx.saved = mod, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        need = ctx.needs_input_grad
+        dx, dx1, pg = Fn.double_conv_bwd(ctx.mod, ctx.saved, g, need_x=need[1], need_x1=need[2])
+        ctx.saved = None
+        pg = [pgi if need[3 + i] else None for i, pgi in enumerate(pg)]
+        return (None, dx if need[1] else None, dx1 if need[2] else None, *pg)
+
+
+class CBAMFn(torch.autograd.Function):
+    @staticmethod
+    def params(mod):
+        ca, sp = mod.channel_att, mod.spatial_att
+        return [ca.MLP[1].weight, ca.MLP[1].bias, ca.MLP[3].weight, ca.MLP[3].bias, sp.conv.weight, sp.bn.weight, sp.bn.bias]
+
+    @staticmethod
+    def run(mod, x):
+        return CBAMFn.apply(mod, x, *CBAMFn.params(mod))
+
+    @staticmethod
+    def forward(ctx, mod, x, *params):
+        out, saved = Fn.cbam_fwd(mod, ops._dense(x, "x"))
+        ctx.mod, ctx.saved = mod, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        dx, pg = Fn.cbam_bwd(ctx.mod, ctx.saved, g)
+        ctx.saved = None
+        need = ctx.needs_input_grad
+        return (None, dx if need[1] else None, *[p if need[2 + i] else None for i, p in enumerate(pg)])
+
+
+class MaxPool2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = ops._dense(x, "x")
+        ctx.save_for_backward(x)
+        return ops.maxpool2(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return Fn.maxpool2_bwd(x, g)
+
+
+class Upsample2xPadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Ho, Wo):
+        ctx.in_shape = tuple(x.shape)
+        return ops.upsample2x_pad(x, Ho, Wo)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Fn.upsample2x_pad_bwd(g, ctx.in_shape), None, None
+
+
+class OutConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = ops._dense(x, "x")
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return ops.outconv(x, weight.detach(), bias.detach() if bias is not None else None)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        dx, dW, db = Fn.outconv_bwd(x, weight, g, need_x=ctx.needs_input_grad[0])
+        return dx, dW, (db if ctx.has_bias else None)

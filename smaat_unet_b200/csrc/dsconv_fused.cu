@@ -32,7 +32,7 @@ struct DsParams {
   const float* shift;
   float* y;
   int64_t y_bstride;
-  float* stats;
+  double* stats;
   int C0, C1, H, W, Cout, relu, K;
   int tiles_x, tiles_y, total_tiles, nchunks;
 };
@@ -264,8 +264,8 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
                 const float mv = pvalid ? pre : 0.f;
                 const float s1 = warp_sum(mv), s2 = warp_sum(mv * mv);
                 if (lane == 0) {
-                  atomicAdd(p.stats + c0 + j, s1);
-                  atomicAdd(p.stats + p.Cout + c0 + j, s2);
+                  atomicAdd(p.stats + c0 + j, (double)s1);
+                  atomicAdd(p.stats + p.Cout + c0 + j, (double)s2);
                 }
               }
               if (pvalid) yp[(int64_t)j * P] = fmaxf(pre, act_lo);
@@ -422,7 +422,7 @@ extern "C" int smaat_dsconv_eligible(const float* x0, int C0, int64_t x0_bstride
 
 extern "C" int smaat_dsconv_fwd(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
                                 const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_w_lo,
-                                const float* scale, const float* shift, float* y, int64_t y_bstride, float* stats, int B, int H,
+                                const float* scale, const float* shift, float* y, int64_t y_bstride, double* stats, int B, int H,
                                 int W, int k, int Cout, int relu, int mode, void* stream) {
   SMAAT_REQUIRE(x0 && dw_w && pw_w && y, "dsconv: null pointer");
   SMAAT_REQUIRE(B > 0 && C0 > 0 && C1 >= 0 && H > 0 && W > 0 && Cout > 0, "dsconv: bad shape");

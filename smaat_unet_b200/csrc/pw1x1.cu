@@ -4,16 +4,16 @@
 
 namespace smaat {
 int pw1x1_simt_launch(const float* x, const float* w, const float* scale, const float* shift, float* y, int64_t y_bstride,
-                      float* stats, int B, int K, int Cout, int P, int relu, cudaStream_t st);
+                      double* stats, int B, int K, int Cout, int P, int relu, cudaStream_t st);
 int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const float* scale, const float* shift, float* y,
-                    int64_t y_bstride, float* stats, int B, int K, int Cout, int P, int relu, bool x3, cudaStream_t st);
+                    int64_t y_bstride, double* stats, int B, int K, int Cout, int P, int relu, bool x3, cudaStream_t st);
 bool pw1x1_tc_eligible(const float* x, const float* w, const float* w_lo, int K, int Cout, int P);
 }  // namespace smaat
 
 using namespace smaat;
 
 extern "C" int smaat_pw1x1_fwd(const float* x, const float* w, const float* w_lo, const float* scale, const float* shift,
-                               float* y, int64_t y_bstride, float* stats, int B, int K, int Cout, int P, int relu, int mode,
+                               float* y, int64_t y_bstride, double* stats, int B, int K, int Cout, int P, int relu, int mode,
                                void* stream) {
   SMAAT_REQUIRE(x && w && y, "pw1x1: null pointer");
   SMAAT_REQUIRE(B > 0 && K > 0 && Cout > 0 && P > 0, "pw1x1: bad shape B=%d K=%d Cout=%d P=%d", B, K, Cout, P);

@@ -17,7 +17,7 @@ constexpr int PW_BK = 16;
 template <bool VECX, bool VECW>
 __global__ void __launch_bounds__(256) pw1x1_simt_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
-                                                         float* __restrict__ y, int64_t y_bstride, float* __restrict__ stats,
+                                                         float* __restrict__ y, int64_t y_bstride, double* __restrict__ stats,
                                                          int K, int Cout, int P, int relu) {
   __shared__ __align__(16) float Xs[PW_BK][PW_BN];
   __shared__ __align__(16) float Ws[PW_BK][PW_BM + 4];
@@ -125,15 +125,15 @@ __global__ void __launch_bounds__(256) pw1x1_simt_kernel(const float* __restrict
       s1 = warp_sum(s1);
       s2 = warp_sum(s2);
       if (tx == 0) {
-        atomicAdd(stats + oo, s1);
-        atomicAdd(stats + Cout + oo, s2);
+        atomicAdd(stats + oo, (double)s1);
+        atomicAdd(stats + Cout + oo, (double)s2);
       }
     }
   }
 }
 
 int pw1x1_simt_launch(const float* x, const float* w, const float* scale, const float* shift, float* y, int64_t y_bstride,
-                      float* stats, int B, int K, int Cout, int P, int relu, cudaStream_t st) {
+                      double* stats, int B, int K, int Cout, int P, int relu, cudaStream_t st) {
   dim3 grid(ceil_div(P, PW_BN), ceil_div(Cout, PW_BM), B);
   SMAAT_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "pw1x1(simt): grid too large");
   const bool vx = (P % 4 == 0) && aligned16(x);

@@ -38,7 +38,7 @@ struct PwTcParams {
   const float* shift;
   float* y;
   int64_t y_bstride;
-  float* stats;
+  double* stats;
   int K, Cout, P, relu;
   int tiles_m, tiles_n, total_tiles;
 };
@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // epilogue affine of the channels this CTA can touch (padded with identity), read back as LDS.128 broadcasts
+  // epilogue affine of the channels this CTA can touch (padded with identity; all-identity when no affine is given,
+  // which is why indices may wrap for Cout > AFF_N), read back as LDS.128 broadcasts
   for (int c = threadIdx.x; c < L::AFF_N; c += blockDim.x) {
     aff[c] = (c < p.Cout && p.scale) ? __ldg(p.scale + c) : 1.f;
     aff[L::AFF_N + c] = (c < p.Cout && p.shift) ? __ldg(p.shift + c) : 0.f;
@@ -211,8 +212,8 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
         float scv[32], shv[32];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 a = *reinterpret_cast<const float4*>(aff + n0 + c0 + 4 * j4);
-          const float4 t = *reinterpret_cast<const float4*>(aff + L::AFF_N + n0 + c0 + 4 * j4);
+          const float4 a = *reinterpret_cast<const float4*>(aff + ((n0 + c0 + 4 * j4) & (L::AFF_N - 1)));
+          const float4 t = *reinterpret_cast<const float4*>(aff + L::AFF_N + ((n0 + c0 + 4 * j4) & (L::AFF_N - 1)));
           scv[4 * j4] = a.x; scv[4 * j4 + 1] = a.y; scv[4 * j4 + 2] = a.z; scv[4 * j4 + 3] = a.w;
           shv[4 * j4] = t.x; shv[4 * j4 + 1] = t.y; shv[4 * j4 + 2] = t.z; shv[4 * j4 + 3] = t.w;
         }
@@ -237,8 +238,8 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
                 const float m = pvalid ? pre : 0.f;
                 const float s1 = warp_sum(m), s2 = warp_sum(m * m);
                 if (lane == 0) {
-                  atomicAdd(p.stats + n0 + c0 + j, s1);
-                  atomicAdd(p.stats + p.Cout + n0 + c0 + j, s2);
+                  atomicAdd(p.stats + n0 + c0 + j, (double)s1);
+                  atomicAdd(p.stats + p.Cout + n0 + c0 + j, (double)s2);
                 }
               }
               if (pvalid) yp[(int64_t)j * p.P] = fmaxf(pre, act_lo);
@@ -312,10 +313,10 @@ bool pw1x1_tc_eligible(const float* x, const float* w, const float* w_lo, int K,
 }
 
 int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const float* scale, const float* shift, float* y,
-                    int64_t y_bstride, float* stats, int B, int K, int Cout, int P, int relu, bool x3, cudaStream_t st) {
+                    int64_t y_bstride, double* stats, int B, int K, int Cout, int P, int relu, bool x3, cudaStream_t st) {
   SMAAT_REQUIRE(pw1x1_tc_eligible(x, w, w_lo, K, Cout, P), "pw1x1(tc): needs P %% 4 == 0, K %% 4 == 0 and 16-byte aligned x/w");
   SMAAT_REQUIRE(!x3 || w_lo, "pw1x1(tc): TF32X3 needs w_lo (see smaat_split_tf32)");
-  SMAAT_REQUIRE(Cout <= 512, "pw1x1(tc): Cout=%d > 512 (epilogue affine staging)", Cout);
+  SMAAT_REQUIRE(Cout <= 512 || (!scale && !shift), "pw1x1(tc): Cout=%d > 512 with an epilogue affine (smem staging holds 512 channels)", Cout);
   const int n_tile = (Cout > 128 && !x3) ? 256 : (Cout > 64 ? 128 : 64);
 
   CUtensorMap mx, mw, mwl;

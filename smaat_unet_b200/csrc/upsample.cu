@@ -1,81 +1,91 @@
 // upsample.cu -- nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True) + F.pad to the skip size
 // (reference models/unet_parts_depthwise_separable.py:64,78-81), forward.
 //
-// Write-bound (output 4x the input).  One CTA produces a 128 x 16 output tile of one (b, c) plane: the
-// <= 66 x 10 source pixels it depends on are staged once in shared memory with coalesced loads, then
-// every thread computes 2 rows x 4 consecutive pixels from smem taps and issues 128-bit stores.  Index
-// math follows torch's area_pixel_compute_source_index for align_corners=True: src = dst*(in-1)/(out-1).
+// Write-bound (output 4x the input).  One thread produces a 2-row x 4-pixel output block: with a source
+// step < 0.5 per output pixel those 8 outputs depend on at most 3 source rows x 4 source columns, which
+// are loaded once (12 loads per 8 outputs instead of 32) from a 4x smaller plane that stays in L1/L2;
+// two 128-bit stores.  grid = (row-pair x quad blocks of one plane, C, B): 32-bit index math only.
+// Index math follows torch's area_pixel_compute_source_index for align_corners=True: src = dst*(in-1)/(out-1).
 #include "common.cuh"
 
 namespace smaat {
 
-constexpr int UP_TW = 128, UP_TH = 16;      // output tile
-constexpr int UP_SW = UP_TW / 2 + 4, UP_SH = UP_TH / 2 + 4;  // source tile bound (scale < 0.5, +2 taps, +slack)
+__device__ __forceinline__ float sel3(int i, float a, float b, float c, float d) {
+  return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : d));
+}
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) upsample2x_pad_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                              int64_t y_bstride, int C, int H, int W, int Ho, int Wo,
-                                                             int pad_t, int pad_l, float ry, float rx, int tiles_x) {
-  __shared__ float src[UP_SH][UP_SW + 1];
-  const int tx0 = (blockIdx.x % tiles_x) * UP_TW;
-  const int ty0 = (blockIdx.x / tiles_x) * UP_TH;
+                                                             int pad_t, int pad_l, float ry, float rx) {
+  const int wq = (Wo + 3) >> 2, hp = (Ho + 1) >> 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= hp * wq) return;
+  const int op = idx / wq;
+  const int oy0 = op << 1;
+  const int ox0 = (idx - op * wq) << 2;
   const int c = blockIdx.y, b = blockIdx.z;
-  const float* xp = x + ((int64_t)b * C + c) * H * W;
-  // source window of this output tile (clamped to the image)
-  const int ux_lo = max(tx0 - pad_l, 0), uy_lo = max(ty0 - pad_t, 0);
-  const int sx0 = min((int)(rx * ux_lo), W - 1), sy0 = min((int)(ry * uy_lo), H - 1);
-  for (int i = threadIdx.x; i < UP_SH * UP_SW; i += 256) {
-    const int r = i / UP_SW, cc = i - r * UP_SW;
-    const int gy = min(sy0 + r, H - 1), gx = min(sx0 + cc, W - 1);  // clamp == the x1/y1 = min(.+1, in-1) rule
-    src[r][cc] = __ldg(xp + (int64_t)gy * W + gx);
-  }
-  __syncthreads();
-  const int tx = threadIdx.x & 31, tyq = threadIdx.x >> 5;
-  const int ox0 = tx0 + 4 * tx;
-  if (ox0 >= Wo) return;
-  float* yp = y + (int64_t)b * y_bstride + (int64_t)c * Ho * Wo;
-  // per-column taps are shared by the two rows this thread produces
-  int cx0[4], cx1[4];
-  float lxv[4];
+  const float* src = x + ((int64_t)b * C + c) * H * W;
+  float* dst = y + (int64_t)b * y_bstride + ((int64_t)c * Ho + oy0) * Wo + ox0;
+
+  // source columns: xa .. xa+3 (clamped) cover every tap of the 4 output pixels
+  const int uxa = max(ox0 - pad_l, 0);
+  const int xa = min((int)(rx * (float)uxa), W - 1);
+  int ci[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ci[i] = min(xa + i, W - 1);
+  int ix0[4];
+  float lx[4];
   bool xin[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int ux = ox0 + j - pad_l;
-    xin[j] = (ux >= 0) && (ux < 2 * W) && (ox0 + j < Wo);
+    xin[j] = (ux >= 0) && (ux < 2 * W);
     const float sx = rx * (float)max(ux, 0);
     const int x0 = min((int)sx, W - 1);
-    lxv[j] = sx - (float)x0;
-    cx0[j] = min(x0 - sx0, UP_SW - 1);
-    cx1[j] = min(min(x0 + 1, W - 1) - sx0, UP_SW - 1);
+    lx[j] = sx - (float)x0;
+    ix0[j] = min(max(x0 - xa, 0), 2);
+  }
+  // source rows: ya .. ya+2 (clamped) cover both output rows
+  const int uya = max(oy0 - pad_t, 0);
+  const int ya = min((int)(ry * (float)uya), H - 1);
+  float v[3][4];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float* rp = src + (int64_t)min(ya + r, H - 1) * W;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[r][i] = __ldg(rp + ci[i]);
   }
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int oy = ty0 + tyq + half * 8;
-    if (oy >= Ho) continue;
+  for (int rr = 0; rr < 2; ++rr) {
+    const int oy = oy0 + rr;
+    if (oy >= Ho) break;
     const int uy = oy - pad_t;
     float o[4] = {0.f, 0.f, 0.f, 0.f};
     if (uy >= 0 && uy < 2 * H) {
       const float sy = ry * (float)uy;
       const int y0 = min((int)sy, H - 1);
       const float ly = sy - (float)y0;
-      const int r0 = min(y0 - sy0, UP_SH - 1), r1 = min(min(y0 + 1, H - 1) - sy0, UP_SH - 1);
+      const int r0 = min(max(y0 - ya, 0), 1);  // y0 - ya is 0 or 1; row r0+1 holds min(y0+1, H-1)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (xin[j]) {
-          const float lx = lxv[j];
+          const float t00 = sel3(ix0[j], r0 ? v[1][0] : v[0][0], r0 ? v[1][1] : v[0][1], r0 ? v[1][2] : v[0][2], r0 ? v[1][3] : v[0][3]);
+          const float t01 = sel3(ix0[j] + 1, r0 ? v[1][0] : v[0][0], r0 ? v[1][1] : v[0][1], r0 ? v[1][2] : v[0][2], r0 ? v[1][3] : v[0][3]);
+          const float t10 = sel3(ix0[j], r0 ? v[2][0] : v[1][0], r0 ? v[2][1] : v[1][1], r0 ? v[2][2] : v[1][2], r0 ? v[2][3] : v[1][3]);
+          const float t11 = sel3(ix0[j] + 1, r0 ? v[2][0] : v[1][0], r0 ? v[2][1] : v[1][1], r0 ? v[2][2] : v[1][2], r0 ? v[2][3] : v[1][3]);
           // same association as torch's upsample_bilinear2d: w_y0*(w_x0*v00 + w_x1*v01) + w_y1*(...)
-          o[j] = (1.f - ly) * ((1.f - lx) * src[r0][cx0[j]] + lx * src[r0][cx1[j]]) +
-                 ly * ((1.f - lx) * src[r1][cx0[j]] + lx * src[r1][cx1[j]]);
+          o[j] = (1.f - ly) * ((1.f - lx[j]) * t00 + lx[j] * t01) + ly * ((1.f - lx[j]) * t10 + lx[j] * t11);
         }
       }
     }
-    float* dst = yp + (int64_t)oy * Wo + ox0;
+    float* d = dst + (int64_t)rr * Wo;
     if (VEC) {
-      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (ox0 + j < Wo) dst[j] = o[j];
+        if (ox0 + j < Wo) d[j] = o[j];
     }
   }
 }
@@ -95,12 +105,11 @@ extern "C" int smaat_upsample2x_pad_fwd(const float* x, float* y, int64_t y_bstr
   const float ry = (2 * H > 1) ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
   const float rx = (2 * W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
   const bool vec = (Wo % 4 == 0) && aligned16(y) && (y_bstride % 4 == 0);
-  const int tiles_x = ceil_div(Wo, UP_TW), tiles_y = ceil_div(Ho, UP_TH);
-  dim3 grid(tiles_x * tiles_y, C, B);
+  dim3 grid(ceil_div(ceil_div(Ho, 2) * ceil_div(Wo, 4), 256), C, B);
   if (vec)
-    upsample2x_pad_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx, tiles_x);
+    upsample2x_pad_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx);
   else
-    upsample2x_pad_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx, tiles_x);
+    upsample2x_pad_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx);
   SMAAT_LAUNCH_CHECK("smaat_upsample2x_pad_fwd");
   return SMAAT_OK;
 }

@@ -26,11 +26,20 @@ def _versions(*tensors):
     return tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
 
 
+def _needs_grad(mod, *inputs):
+    """True when the call must be recorded on the autograd tape (grad mode on and a parameter or input requires grad)."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(isinstance(t, torch.Tensor) and t.requires_grad for t in inputs):
+        return True
+    return any(p.requires_grad for p in mod.parameters())
+
+
 def _no_autograd(mod, *inputs):
-    if torch.is_grad_enabled() and mod.training:
+    if _needs_grad(mod, *inputs):
         raise NotImplementedError(
-            f"{type(mod).__name__}: train-mode forward with autograd is not implemented in this build of "
-            "smaat_unet_b200 (forward/eval only). Call .eval() and/or torch.no_grad(); no PyTorch fallback is provided.")
+            f"{type(mod).__name__}: autograd through this standalone module is not implemented in smaat_unet_b200 "
+            "(DoubleConvDS / DownDS / UpDS / CBAM / OutConv are differentiable). Use torch.no_grad(); no PyTorch fallback is provided.")
 
 
 class DepthwiseSeparableConv(nn.Module):
@@ -118,18 +127,19 @@ class DoubleConvDS(nn.Module):
 
     def run(self, x, x1=None):
         ops._req(x, "input", 4)
-        if self.training:
-            raise NotImplementedError("DoubleConvDS: train-mode (batch-statistics) forward is not implemented in this build")
-        for bn in (self.double_conv[1], self.double_conv[4]):
-            if not bn.track_running_stats or bn.running_mean is None:
-                raise NotImplementedError("BatchNorm2d without running statistics is not supported")
+        if _needs_grad(self, x, x1):
+            from .autograd import DoubleConvDSFn
+            return DoubleConvDSFn.run(self, x, x1)
+        bns = (self.double_conv[1], self.double_conv[4])
+        if self.training or any(not bn.track_running_stats or bn.running_mean is None for bn in bns):
+            from . import functional as Fn       # batch statistics (and running-stat update), no tape
+            return Fn.double_conv_fwd(self, x, x1)[0]
         s0, t0 = self._folded(0)
         y = self.double_conv[0].run(x, x1=x1, scale=s0, shift=t0, relu=True)
         s1, t1 = self._folded(3)
         return self.double_conv[3].run(y, scale=s1, shift=t1, relu=True)
 
     def forward(self, x):
-        _no_autograd(self, x)
         return self.run(x)
 
 
@@ -144,8 +154,12 @@ class DownDS(nn.Module):
         )
 
     def forward(self, x):
-        _no_autograd(self, x)
-        return self.maxpool_conv[1].run(ops.maxpool2(x))
+        if _needs_grad(self, x):
+            from .autograd import MaxPool2Fn
+            pooled = MaxPool2Fn.apply(x) if x.requires_grad else ops.maxpool2(x)
+        else:
+            pooled = ops.maxpool2(x)
+        return self.maxpool_conv[1].run(pooled)
 
 
 class UpDS(nn.Module):
@@ -165,11 +179,14 @@ class UpDS(nn.Module):
             self.conv = DoubleConvDS(in_channels, out_channels, kernels_per_layer=kernels_per_layer)
 
     def forward(self, x1, x2):
-        _no_autograd(self, x1, x2)
         if not self.bilinear:
             raise NotImplementedError("UpDS(bilinear=False) (ConvTranspose2d upsampling, parts_ds.py:72-73) is not "
                                       "implemented in this build; the SmaAt-UNet configs use bilinear=True")
-        up = ops.upsample2x_pad(x1, x2.shape[2], x2.shape[3])
+        if torch.is_grad_enabled() and x1.requires_grad:
+            from .autograd import Upsample2xPadFn
+            up = Upsample2xPadFn.apply(x1, x2.shape[2], x2.shape[3])
+        else:
+            up = ops.upsample2x_pad(x1, x2.shape[2], x2.shape[3])
         return self.conv.run(x2, x1=up)
 
 
@@ -181,7 +198,9 @@ class OutConv(nn.Module):
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
 
     def forward(self, x):
-        _no_autograd(self, x)
+        if _needs_grad(self, x):
+            from .autograd import OutConvFn
+            return OutConvFn.apply(x, self.conv.weight, self.conv.bias)
         return ops.outconv(x, self.conv.weight.detach(), self.conv.bias.detach() if self.conv.bias is not None else None)
 
 
@@ -233,8 +252,9 @@ class SpatialAttention(nn.Module):
 
     def bn_affine(self):
         """Device tensor [scale, shift] of the eval-mode BatchNorm2d(1); cached."""
-        if self.training:
-            raise NotImplementedError("SpatialAttention: train-mode (batch-statistics) forward is not implemented in this build")
+        if self.bn.training:
+            raise NotImplementedError("standalone SpatialAttention in train mode is not implemented (CBAM handles it); "
+                                      "call .eval() or use CBAM")
         bn = self.bn
         key = _versions(bn.weight, bn.bias, bn.running_mean, bn.running_var)
         if self._fold is None or self._fold[0] != key:
@@ -262,7 +282,12 @@ class CBAM(nn.Module):
         self.spatial_att = SpatialAttention(kernel_size=kernel_size)
 
     def forward(self, x, out=None):
-        _no_autograd(self, x)
+        if _needs_grad(self, x):
+            from .autograd import CBAMFn
+            return CBAMFn.run(self, x)
+        if self.spatial_att.bn.training or not self.spatial_att.bn.track_running_stats:
+            from . import functional as Fn       # batch statistics for the gate's BatchNorm2d(1), no tape
+            return Fn.cbam_fwd(self, ops._dense(x, "x"))[0]
         sc = self.channel_att.gate(x)
         sa = self.spatial_att.gate(x, sc)
         return ops.cbam_scale(x, sc, sa, out=out)

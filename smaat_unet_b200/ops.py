@@ -217,6 +217,52 @@ def bn_fold(gamma, beta, running_mean, running_var, conv_bias, eps):
     return scale, shift
 
 
+def new_stats(C, device):
+    """Zeroed fp64 accumulators [sum(C) | sum of squares(C)] for the train-mode BN epilogues."""
+    return torch.zeros(2 * C, device=device, dtype=torch.float64)
+
+
+def channel_stats(x, stats=None):
+    x = _dense(x, "x")
+    B, Cc, H, W = x.shape
+    if stats is None:
+        stats = new_stats(Cc, x.device)
+    _call("smaat_channel_stats", 4 * B * Cc * H * W, 0, _lib.load().smaat_channel_stats, _ptr(x), _ptr(stats), B, Cc, H * W, _stream())
+    return stats
+
+
+def bn_finalize(stats, count, bn, save=False):
+    """Batch statistics -> (scale, shift) [, mean, invstd]; updates bn.running_mean/var in place (torch semantics)."""
+    Cn = bn.num_features
+    dev = stats.device
+    scale = torch.empty(Cn, device=dev, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    mean = torch.empty_like(scale) if save else None
+    invstd = torch.empty_like(scale) if save else None
+    track = bn.track_running_stats and bn.running_mean is not None
+    if track and bn.momentum is None:
+        raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative average) is not supported")
+    _call("smaat_bn_finalize", 40 * Cn, 0, _lib.load().smaat_bn_finalize, _ptr(stats), float(count),
+          _ptr(bn.weight.detach() if bn.weight is not None else None), _ptr(bn.bias.detach() if bn.bias is not None else None),
+          float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1),
+          _ptr(bn.running_mean if track else None), _ptr(bn.running_var if track else None),
+          _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), Cn, _stream())
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return (scale, shift, mean, invstd) if save else (scale, shift)
+
+
+def affine_act(x, scale, shift, act):
+    """y = act(scale[c]*x + shift[c]); act in {'none','relu','sigmoid'}."""
+    x = _dense(x, "x")
+    B, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    code = {"none": 0, "relu": 1, "sigmoid": 2}[act]
+    _call("smaat_affine_act_fwd", 8 * B * Cc * H * W, 0, _lib.load().smaat_affine_act_fwd, _ptr(x), _ptr(scale), _ptr(shift), _ptr(y),
+          B, Cc, H * W, code, _stream())
+    return y
+
+
 def maxpool2(x):
     """nn.MaxPool2d(2) (parts_ds.py:48)."""
     x = _dense(x, "x")

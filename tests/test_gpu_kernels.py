@@ -114,7 +114,7 @@ def test_pw1x1_stats_and_strided_output(mode):
     B, K, Cout, H, W = 2, 64, 48, 12, 12
     x, w, bias = rnd(B, K, H, W), rnd(Cout, K, 1, 1, lo=-0.3, hi=0.3), rnd(Cout)
     pre = O.pointwise1x1(x.astype(np.float64), w, bias)
-    stats = torch.zeros(2 * Cout, device="cuda")
+    stats = torch.zeros(2 * Cout, device="cuda", dtype=torch.float64)
     wide = torch.zeros(B, Cout + 8, H, W, device="cuda")
     out = wide[:, 8:]
     ops.pw1x1(dev(x), dev(w), None, dev(bias), False, mode=mode, stats=stats, out=out)
@@ -225,7 +225,7 @@ def test_dsconv_fused_matches_oracle(case, mode):
     torch.cuda.synchronize()
     assert_close(y, ref, PW_TOL[mode], f"dsconv {mode} {case}")
     # no bias / no affine / no relu + statistics
-    stats = torch.zeros(2 * Cout, device="cuda")
+    stats = torch.zeros(2 * Cout, device="cuda", dtype=torch.float64)
     y2 = ops.dsconv(x0, dev(dw_w), None, k, dev(pw_w), None, None, False, x1=x1, mode=mode, stats=stats)
     pre = O.pointwise1x1(O.depthwise3x3(x.astype(np.float64), dw_w, None, k), pw_w, None)
     assert_close(y2, pre, PW_TOL[mode], f"dsconv plain {mode} {case}")

@@ -1,0 +1,152 @@
+"""-m gpu: train-mode forward (batch-statistics BatchNorm, running-stat updates) vs the reference's golden
+outputs, and every gradient of the differentiable blocks vs torch autograd over the CPU port (float64)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import smaat_unet_b200 as S
+from oracle import torch_port as TP
+from oracle.cases import CASES, case_tensors
+from tests._util import assert_close, dev, load_np_state_dict
+from tests.test_gpu_modules import build
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TRAIN_CASES = sorted(n for n, c in CASES.items() if c.get("train", False))
+# train-mode BatchNorm divides by the batch std: fp32 noise is amplified (reference self-noise 2e-5)
+FWD_TOL = {"fp32": 2e-4, "tf32x3": 2e-4}
+GRAD_TOL = 5e-4
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_train_forward_matches_reference_golden(name, mode):
+    c = CASES[name]
+    sd, xs = case_tensors(name, np.float32)
+    mod, prefix = build(c)
+    load_np_state_dict(mod, sd, prefix)
+    mod = mod.cuda().train()
+    S.set_pointwise_mode(mode)
+    try:
+        with torch.no_grad():
+            y = mod(*[dev(x) for x in xs])
+        torch.cuda.synchronize()
+    finally:
+        S.set_pointwise_mode("tf32x3")
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    assert_close(y, g["output"], FWD_TOL[mode], f"{name} train fwd [{mode}]")
+    after = mod.state_dict()
+    for key in g.files:                      # running_mean / running_var / num_batches_tracked after one step
+        if key.startswith("buf:"):
+            k2 = key[4:][len(prefix):] if prefix else key[4:]
+            got = after[k2].double().cpu().numpy()
+            ref = g[key].astype(np.float64)
+            assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), key
+
+
+def _cpu_reference(kind, c, sd_np, xs_np, train, R):
+    """float64 torch autograd over the CPU port: returns (output, dict name -> grad, [input grads])."""
+    sd = {}
+    for k, v in sd_np.items():
+        t = torch.as_tensor(np.asarray(v))
+        sd[k] = t.double().requires_grad_(True) if t.dtype != torch.int64 and not k.endswith(("running_mean", "running_var")) \
+            else (t.double() if t.dtype != torch.int64 else t)
+    xs = [torch.from_numpy(x).double().requires_grad_(True) for x in xs_np]
+    if kind == "doubleconv":
+        y = TP.double_conv_ds(xs[0], sd, "m", train)
+    elif kind == "down":
+        y = TP.down_ds(xs[0], sd, "m", train)
+    elif kind == "up":
+        y = TP.up_ds(xs[0], xs[1], sd, "m", train)
+    elif kind == "cbam":
+        y = TP.cbam(xs[0], sd, "m", train)
+    elif kind == "outconv":
+        y = torch.nn.functional.conv2d(xs[0], sd["m.conv.weight"], sd["m.conv.bias"])
+    elif kind == "unet":
+        y = TP.smaat_unet_forward(xs[0], sd, train)
+    else:
+        raise KeyError(kind)
+    (y * torch.from_numpy(R)).sum().backward()
+    grads = {k: v.grad.numpy() for k, v in sd.items() if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None}
+    return y.detach().numpy(), grads, [x.grad.numpy() for x in xs]
+
+
+GRAD_CASES = ["doubleconv_eval", "doubleconv_mid_eval", "doubleconv_train", "down_eval", "up_eval_even", "up_eval_pad",
+              "cbam_k7_eval", "cbam_k3_eval", "cbam_k7_train", "outconv", "unet_12_1_k2_32", "unet_12_1_k2_train", "unet_3_5_k1_48"]
+
+
+@pytest.mark.parametrize("train", [False, True])
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_gradients_match_cpu_autograd(name, train):
+    c = CASES[name]
+    kind = c["kind"]
+    if kind == "outconv" and train:
+        pytest.skip("no mode dependence")
+    sd_np, xs_np = case_tensors(name, np.float64)
+    mod, prefix = build(c)
+    load_np_state_dict(mod, {k: np.asarray(v, dtype=np.float32) if np.asarray(v).dtype != np.int64 else v for k, v in sd_np.items()}, prefix)
+    mod = mod.cuda().train(train)
+    xs = [dev(x).requires_grad_(True) for x in xs_np]
+    y = mod(*xs)
+    assert y.requires_grad, "output is not attached to the autograd tape"
+    R = np.random.default_rng(77).uniform(-1, 1, tuple(y.shape))
+    (y * dev(R)).sum().backward()
+    torch.cuda.synchronize()
+    y_ref, g_ref, gx_ref = _cpu_reference(kind, c, sd_np, xs_np, train, R)
+    assert_close(y, y_ref, 3e-4, f"{name} forward (train={train})")
+    # Full networks in train mode on these tiny frames normalise the bottleneck with batch statistics over
+    # n = B*2*2 = 8 values: ill-conditioned -- the reference itself moves by ~1e-2 between fp32 and fp64
+    # (measured on the CPU port: dx 1.2e-2, dW 9e-3 for unet_12_1_k2_32).  There the max-norm bound is
+    # loosened and a relative L2 bound added; every per-block case keeps the tight bound.
+    loose = kind == "unet" and train
+    gtol = 4e-2 if loose else GRAD_TOL
+
+    def rel_l2(got, ref):
+        got = got.detach().double().cpu().numpy()
+        return float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
+
+    for x, gr in zip(xs, gx_ref):
+        assert x.grad is not None
+        assert_close(x.grad, gr, gtol, f"{name} d/d(input) (train={train})")
+        assert rel_l2(x.grad, gr) <= (2e-2 if loose else 1e-3)
+    named = dict(mod.named_parameters())
+    checked = 0
+    for k, gr in g_ref.items():
+        pk = k[len(prefix):] if prefix else k
+        p = named[pk]
+        assert p.grad is not None, f"no gradient for {pk}"
+        if np.abs(gr).max() < 1e-12:
+            assert float(p.grad.abs().max()) < 2e-4, pk   # exactly-zero gradients (conv bias before a train-mode BN): only noise
+        else:
+            assert_close(p.grad, gr, gtol, f"{name} d/d({pk}) (train={train})")
+        checked += 1
+    assert checked == len(named)
+
+
+def test_training_step_reduces_loss_and_matches_cpu_one_step():
+    """One Adam step on the reference's loss (regression_lightning.py:57-65: mse(sum)/B) moves the parameters the same
+    way on the B200 path and on the CPU port."""
+    name = "unet_12_1_k2_train"
+    sd_np, xs_np = case_tensors(name, np.float64)
+    tgt = np.random.default_rng(5).uniform(0, 1, (xs_np[0].shape[0], 32, 32))
+    model = load_np_state_dict(S.SmaAt_UNet(12, 1, kernels_per_layer=2), {k: (np.asarray(v, np.float32) if np.asarray(v).dtype != np.int64 else v)
+                                                                          for k, v in sd_np.items()}).cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    x, t = dev(xs_np[0]), dev(tgt)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        pred = model(x)
+        loss = torch.nn.functional.mse_loss(pred.squeeze(1), t, reduction="sum") / x.shape[0]
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[2] < losses[0]
+    # CPU port, same 1st-step loss
+    sd = TP.to_torch_sd(sd_np, torch.float64)
+    with torch.no_grad():
+        p0 = TP.smaat_unet_forward(torch.from_numpy(xs_np[0]), sd, True)
+    l0 = float(torch.nn.functional.mse_loss(p0.squeeze(1), torch.from_numpy(tgt), reduction="sum") / x.shape[0])
+    assert abs(losses[0] - l0) <= 1e-3 * abs(l0)
