@@ -184,6 +184,10 @@ int smaat_dw3x3_bwd_weight(const float* dd, const float* x0, int C0, int64_t x0_
 /* pointwise 1x1: dW[o][c] += sum_{b,p} dz[b,o,p]*d[b,c,p], db[o] += sum dz.  (The input gradient is
  * smaat_pw1x1_fwd(dz, W^T): use smaat_transpose for W^T.) */
 int smaat_pw1x1_bwd_weight(const float* dz, const float* d, float* dW, float* db, int B, int K, int Cout, int P, void* stream);
+/* tensor-core (tcgen05, split over pixels + fp32 atomics) variant; mode SMAAT_PW_TF32 / SMAAT_PW_TF32X3;
+ * SMAAT_E_UNSUPPORTED when P % 4 != 0 (use the CUDA-core smaat_pw1x1_bwd_weight). */
+int smaat_pw1x1_bwd_weight_tc(const float* dz, const float* d, float* dW, float* db, int B, int K, int Cout, int P,
+                              int mode, void* stream);
 int smaat_transpose(const float* src, float* dst, int rows, int cols, void* stream);
 
 int smaat_maxpool2_bwd(const float* x, const float* dy, float* dx, int64_t N, int H, int W, void* stream);

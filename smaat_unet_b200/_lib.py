@@ -44,6 +44,7 @@ SIGNATURES = {
     "smaat_dw3x3_bwd_input": [_p, _p, _p, _i, _l, _p, _i, _l, _i, _i, _i, _i, _p],
     "smaat_dw3x3_bwd_weight": [_p, _p, _i, _l, _p, _i, _l, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "smaat_pw1x1_bwd_weight": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "smaat_pw1x1_bwd_weight_tc": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "smaat_transpose": [_p, _p, _i, _i, _p],
     "smaat_maxpool2_bwd": [_p, _p, _p, _l, _i, _i, _p],
     "smaat_upsample2x_pad_bwd": [_p, _l, _p, _i, _i, _i, _i, _i, _i, _p],

@@ -76,11 +76,11 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const float* __re
                                                                const float* __restrict__ a, const float* __restrict__ b,
                                                                const float* __restrict__ cc, float* __restrict__ dz, int C, int P,
                                                                int act) {
-  const int plane = blockIdx.y, c = plane % C;
+  const int plane = blockIdx.x, c = plane % C;
   const float s = scale ? __ldg(scale + c) : 1.f, t = shift ? __ldg(shift + c) : 0.f;
   const float av = __ldg(a + c), bv = __ldg(b + c), cv = __ldg(cc + c);
   const int64_t base = (int64_t)plane * P;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P; i += gridDim.y * blockDim.x) {
     const float zv = __ldg(z + base + i);
     float g = __ldg(dy + base + i);
     if (act == 1 && !(fmaf(zv, s, t) > 0.f)) g = 0.f;
@@ -361,6 +361,14 @@ __global__ void __launch_bounds__(256) outconv_bwd_weight_kernel(const float* __
 
 }  // namespace smaat
 
+namespace smaat {
+int dw3x3_bwd_input_tiled_launch(const float* dd, const float* w, float* dx0, int C0, int64_t bs0, float* dx1, int C1, int64_t bs1,
+                                 int B, int H, int W, int k, cudaStream_t st);
+int dw3x3_bwd_weight_tiled_launch(const float* dd, const float* x0, int C0, int64_t bs0, const float* x1, int C1, int64_t bs1,
+                                  const float* in_scale, const float* in_shift, float* dw, float* db, int B, int H, int W, int k,
+                                  cudaStream_t st);
+}  // namespace smaat
+
 using namespace smaat;
 
 static inline unsigned grid1d(int64_t items, int threads, int cap_mult = 32) {
@@ -396,8 +404,9 @@ extern "C" int smaat_bn_bwd_coeffs(const double* sums, double count, const float
 extern "C" int smaat_bn_act_bwd_apply(const float* dy, const float* z, const float* scale, const float* shift, const float* a,
                                       const float* b, const float* cc, float* dz, int B, int C, int P, int act, void* stream) {
   SMAAT_REQUIRE(dy && z && a && b && cc && dz && B > 0 && C > 0 && P > 0, "bn_act_bwd_apply: bad arguments");
-  SMAAT_REQUIRE((int64_t)B * C <= 65535, "bn_act_bwd_apply: B*C too large for grid.y");
-  dim3 grid(grid1d(P, 256, 4), B * C);
+  unsigned gy = grid1d(P, 256, 4);
+  if (gy > 65535u) gy = 65535u;
+  dim3 grid(B * C, gy);
   bn_act_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, z, scale, shift, a, b, cc, dz, C, P, act);
   SMAAT_LAUNCH_CHECK("smaat_bn_act_bwd_apply");
   return SMAAT_OK;
@@ -407,6 +416,7 @@ extern "C" int smaat_dw3x3_bwd_input(const float* dd, const float* w, float* dx0
                                      int64_t dx1_bstride, int B, int H, int W, int k, void* stream) {
   SMAAT_REQUIRE(dd && w && dx0 && B > 0 && C0 > 0 && C1 >= 0 && H > 0 && W > 0 && k > 0, "dw3x3_bwd_input: bad arguments");
   SMAAT_REQUIRE(C1 == 0 || dx1, "dw3x3_bwd_input: C1 > 0 but dx1 null");
+  if (k <= 4) return dw3x3_bwd_input_tiled_launch(dd, w, dx0, C0, dx0_bstride, dx1, C1, dx1_bstride, B, H, W, k, (cudaStream_t)stream);
   SMAAT_REQUIRE((int64_t)B * (C0 + C1) <= 65535 * 32767ll, "dw3x3_bwd_input: too many planes");
   const int64_t planes = (int64_t)B * (C0 + C1);
   SMAAT_REQUIRE(planes <= 65535, "dw3x3_bwd_input: B*Cin > 65535 not supported yet");
@@ -420,6 +430,9 @@ extern "C" int smaat_dw3x3_bwd_weight(const float* dd, const float* x0, int C0, 
                                       int64_t x1_bstride, const float* in_scale, const float* in_shift, float* dw, float* db, int B,
                                       int H, int W, int k, void* stream) {
   SMAAT_REQUIRE(dd && x0 && dw && B > 0 && C0 > 0 && C1 >= 0 && H > 0 && W > 0 && k > 0, "dw3x3_bwd_weight: bad arguments");
+  if (k <= 4)
+    return dw3x3_bwd_weight_tiled_launch(dd, x0, C0, x0_bstride, x1, C1, x1_bstride, in_scale, in_shift, dw, db, B, H, W, k,
+                                         (cudaStream_t)stream);
   const int KC = k * (C0 + C1);
   SMAAT_REQUIRE(KC <= 65535, "dw3x3_bwd_weight: too many channels");
   const int chunks = pick_chunks((int64_t)B * H * W, KC);

@@ -37,12 +37,12 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, float* __restrict__ y, int C, int P,
                                                          int act) {
-  const int plane = blockIdx.y;  // b * C + c
+  const int plane = blockIdx.x;  // b * C + c
   const int c = plane % C;
   const float s = scale ? __ldg(scale + c) : 1.f, t = shift ? __ldg(shift + c) : 0.f;
   const float* xp = x + (int64_t)plane * P;
   float* yp = y + (int64_t)plane * P;
-  const int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int i4 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   if (i4 >= P) return;
   float v[4];
   if (VEC) {
@@ -123,9 +123,9 @@ extern "C" int smaat_bn_finalize(const double* stats, double count, const float*
 extern "C" int smaat_affine_act_fwd(const float* x, const float* scale, const float* shift, float* y, int B, int C, int P,
                                     int act, void* stream) {
   SMAAT_REQUIRE(x && y && B > 0 && C > 0 && P > 0 && act >= 0 && act <= 2, "affine_act: bad arguments");
-  SMAAT_REQUIRE((int64_t)B * C <= 65535, "affine_act: B*C too large for grid.y");
+  SMAAT_REQUIRE(ceil_div(ceil_div(P, 4), 256) <= 65535, "affine_act: plane too large for grid.y");
   const bool vec = (P % 4 == 0) && aligned16(x) && aligned16(y);
-  dim3 grid(ceil_div(ceil_div(P, 4), 256), B * C);
+  dim3 grid(B * C, ceil_div(ceil_div(P, 4), 256));
   if (vec) affine_act_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, scale, shift, y, C, P, act);
   else affine_act_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, scale, shift, y, C, P, act);
   SMAAT_LAUNCH_CHECK("smaat_affine_act_fwd");

@@ -257,18 +257,20 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
           }
         } else {
 #pragma unroll
+          float m1[32], m2[32];
+#pragma unroll
           for (int j = 0; j < 32; ++j) {
-            if (j < nchn) {
-              const float pre = fmaf(__uint_as_float(r[j]), scv[j], shv[j]);
-              if (p.stats) {
-                const float mv = pvalid ? pre : 0.f;
-                const float s1 = warp_sum(mv), s2 = warp_sum(mv * mv);
-                if (lane == 0) {
-                  atomicAdd(p.stats + c0 + j, (double)s1);
-                  atomicAdd(p.stats + p.Cout + c0 + j, (double)s2);
-                }
-              }
-              if (pvalid) yp[(int64_t)j * P] = fmaxf(pre, act_lo);
+            const float pre = fmaf(__uint_as_float(r[j]), scv[j], shv[j]);
+            const float mv = (pvalid && j < nchn) ? pre : 0.f;
+            m1[j] = mv;
+            m2[j] = mv * mv;
+            if (pvalid && j < nchn) yp[(int64_t)j * P] = fmaxf(pre, act_lo);
+          }
+          if (p.stats) {  // BatchNorm batch statistics: 31-shuffle transpose-reduce, one fp64 atomic per channel
+            const float s1 = warp_transpose_sum32(m1, lane), s2 = warp_transpose_sum32(m2, lane);
+            if (lane < nchn) {
+              atomicAdd(p.stats + c0 + lane, (double)s1);
+              atomicAdd(p.stats + p.Cout + c0 + lane, (double)s2);
             }
           }
         }

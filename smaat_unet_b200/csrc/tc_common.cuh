@@ -81,4 +81,21 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
+// v[j] = this lane's value for channel j (32 channels).  Returns, in lane L, the sum over the 32 lanes of
+// channel L: a butterfly that halves the live channels per step -- 16+8+4+2+1 = 31 shuffles instead of
+// 32 x 5 for 32 independent warp reductions.  (Train-mode BatchNorm statistics in the GEMM epilogues.)
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = up ? v[i + s] : v[i];
+      const float send = up ? v[i] : v[i + s];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
 }  // namespace smaat

@@ -113,12 +113,15 @@ def test_gradients_match_cpu_autograd(name, train):
         assert rel_l2(x.grad, gr) <= (2e-2 if loose else 1e-3)
     named = dict(mod.named_parameters())
     checked = 0
+    gmax_all = max(float(np.abs(gr).max()) for gr in g_ref.values())
     for k, gr in g_ref.items():
         pk = k[len(prefix):] if prefix else k
         p = named[pk]
         assert p.grad is not None, f"no gradient for {pk}"
-        if np.abs(gr).max() < 1e-12:
-            assert float(p.grad.abs().max()) < 2e-4, pk   # exactly-zero gradients (conv bias before a train-mode BN): only noise
+        if np.abs(gr).max() < 1e-6 * gmax_all:
+            # mathematically zero gradients (a conv bias feeding a train-mode BatchNorm is cancelled by the mean
+            # subtraction): both sides hold only summation noise -- bound it relative to the real gradients
+            assert float(p.grad.abs().max()) <= (5e-3 if loose else 1e-3) * gmax_all, pk
         else:
             assert_close(p.grad, gr, gtol, f"{name} d/d({pk}) (train={train})")
         checked += 1
