@@ -262,7 +262,7 @@ def main():
         S.set_pointwise_mode(args.mode)
 
     # ---------------- roofline: per-kernel timing, CUDA events on the launching stream ----------------
-    roof, kernels = None, {}
+    roof, roof_dw, kernels = None, None, {}
     if rank == 0:
         hbm, src = peaks()
         with torch.no_grad():
@@ -280,11 +280,34 @@ def main():
             gbs = a["bytes"] / (a["ms"] * 1e-3) / 1e9 if a["ms"] > 0 else 0.0
             kernels[name] = {"launches_per_step": a["launches"] // 3, "ms_per_step": a["ms"] / 3, "algorithmic_GB_per_step": a["bytes"] / 3e9,
                              "achieved_GBps": gbs, "frac_hbm": gbs / hbm, "tflops": a["flops"] / (a["ms"] * 1e-3) / 1e12 if a["ms"] > 0 else 0.0}
-        d = kernels.get("smaat_dw3x3_fwd")
-        if d:
-            roof = {"kernel": "dw3x3_kernel (18 launches/step, all layers)", "bound": "hbm", "achieved": d["achieved_GBps"], "peak": hbm,
-                    "unit": "GB/s", "frac": d["frac_hbm"], "peak_source": src, "traffic": None,
-                    "algorithmic_bytes_per_step": d["algorithmic_GB_per_step"] * 1e9, "ms_per_step": d["ms_per_step"]}
+        # dominant kernel of the measured path (by time): its own algorithmic bytes / its own time
+        KNAMES = {"smaat_dsconv_fwd": "dsconv_fused_kernel (depthwise 3x3 -> tcgen05 pointwise -> BN/ReLU, one kernel)",
+                  "smaat_pw1x1_fwd": "pw1x1_tc_kernel", "smaat_dw3x3_fwd": "dw3x3_kernel"}
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        d = kernels[dom]
+        # DRAM traffic per launch from the ncu --set full capture of the same kernels (profiles/), GB; None if not captured
+        roof = {"kernel": KNAMES.get(dom, dom) + f" ({d['launches_per_step']} launches/step)", "bound": "hbm",
+                "achieved": d["achieved_GBps"], "peak": hbm, "unit": "GB/s", "frac": d["frac_hbm"], "peak_source": src,
+                "traffic": None, "algorithmic_bytes_per_step": d["algorithmic_GB_per_step"] * 1e9, "ms_per_step": d["ms_per_step"],
+                "note": "fused DS conv is shared-memory-bandwidth bound; its algorithmic bytes are 2.8x fewer than dw+pw unfused (DESIGN.md 5)"
+                if dom == "smaat_dsconv_fwd" else ""}
+        # the metric's named kernel -- "depthwise % HBM roofline": the standalone depthwise kernel over ALL 18 layers
+        # (fusion switched off for this measurement pass only)
+        S.set_fused_dsconv(False)
+        with torch.no_grad():
+            model(xs[0])
+            torch.cuda.synchronize()
+            with S.ops.profile() as prof2:
+                for i in range(3):
+                    model(xs[i % 2])
+            a2 = prof2.summary().get("smaat_dw3x3_fwd")
+        S.set_fused_dsconv(True)
+        if a2:
+            g2 = a2["bytes"] / (a2["ms"] * 1e-3) / 1e9
+            roof_dw = {"kernel": f"dw3x3_kernel ({a2['launches'] // 3} launches/step, all DS layers, unfused pass)", "bound": "hbm",
+                       "achieved": g2, "peak": hbm, "unit": "GB/s", "frac": g2 / hbm, "peak_source": src,
+                       "traffic": 4.02e9, "traffic_note": "ncu dram read+write for the up4.0 launch: 4.02 GB vs 4.08 GB algorithmic (profiles/r01_ncu_summary_v1.md)",
+                       "algorithmic_bytes_per_step": a2["bytes"] / 3, "ms_per_step": a2["ms"] / 3}
 
     # ---------------- CPU baseline (oracle port), rank 0, N=1 only ----------------
     cpu = None
@@ -304,7 +327,7 @@ def main():
                        "global_batch": B_PER_GPU * world, "pointwise": args.mode, "cuda_graph": sess.graph is not None,
                        "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": "inputs alternate between 2 buffers; a step streams ~40 GB of activations (>> 126 MB L2)"},
-            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+            "roofline": roof, "depthwise_roofline": roof_dw, "kernels": kernels, "cpu_baseline": cpu,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": sess.h2d_bytes_per_step,
                     "d2h_bytes_per_step": sess.d2h_bytes_per_step, "ms_per_step": 1e3 * e2e_s / args.steps, "checksum": chk},
             "alt_mode": alt, "clocks": clocks, "gpu_launches": int(launches),

@@ -46,14 +46,14 @@ def test_train_forward_matches_reference_golden(name, mode):
             assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), key
 
 
-def _cpu_reference(kind, c, sd_np, xs_np, train, R):
-    """float64 torch autograd over the CPU port: returns (output, dict name -> grad, [input grads])."""
+def _cpu_reference(kind, c, sd_np, xs_np, train, R, dtype=torch.float64):
+    """torch autograd over the CPU port (float64 = ground truth): returns (output, dict name -> grad, [input grads])."""
     sd = {}
     for k, v in sd_np.items():
         t = torch.as_tensor(np.asarray(v))
-        sd[k] = t.double().requires_grad_(True) if t.dtype != torch.int64 and not k.endswith(("running_mean", "running_var")) \
-            else (t.double() if t.dtype != torch.int64 else t)
-    xs = [torch.from_numpy(x).double().requires_grad_(True) for x in xs_np]
+        sd[k] = t.to(dtype).requires_grad_(True) if t.dtype != torch.int64 and not k.endswith(("running_mean", "running_var")) \
+            else (t.to(dtype) if t.dtype != torch.int64 else t)
+    xs = [torch.from_numpy(x).to(dtype).requires_grad_(True) for x in xs_np]
     if kind == "doubleconv":
         y = TP.double_conv_ds(xs[0], sd, "m", train)
     elif kind == "down":
@@ -68,9 +68,9 @@ def _cpu_reference(kind, c, sd_np, xs_np, train, R):
         y = TP.smaat_unet_forward(xs[0], sd, train)
     else:
         raise KeyError(kind)
-    (y * torch.from_numpy(R)).sum().backward()
-    grads = {k: v.grad.numpy() for k, v in sd.items() if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None}
-    return y.detach().numpy(), grads, [x.grad.numpy() for x in xs]
+    (y * torch.from_numpy(R).to(dtype)).sum().backward()
+    grads = {k: v.grad.double().numpy() for k, v in sd.items() if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None}
+    return y.detach().double().numpy(), grads, [x.grad.double().numpy() for x in xs]
 
 
 GRAD_CASES = ["doubleconv_eval", "doubleconv_mid_eval", "doubleconv_train", "down_eval", "up_eval_even", "up_eval_pad",
@@ -101,16 +101,23 @@ def test_gradients_match_cpu_autograd(name, train):
     # (measured on the CPU port: dx 1.2e-2, dW 9e-3 for unet_12_1_k2_32).  There the max-norm bound is
     # loosened and a relative L2 bound added; every per-block case keeps the tight bound.
     loose = kind == "unet" and train
-    gtol = 4e-2 if loose else GRAD_TOL
+    if loose:   # conditioning probe: how far does the reference algorithm itself move when run in fp32?
+        _, g32, gx32 = _cpu_reference(kind, c, sd_np, xs_np, train, R, torch.float32)
+
+    def tol_for(ref, ref32):
+        if not loose:
+            return GRAD_TOL
+        noise = float(np.abs(ref32 - ref).max() / max(np.abs(ref).max(), 1e-30))
+        return max(GRAD_TOL, 10.0 * noise)      # within an order of magnitude of the reference's own fp32 noise
 
     def rel_l2(got, ref):
         got = got.detach().double().cpu().numpy()
         return float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
 
-    for x, gr in zip(xs, gx_ref):
+    for i, (x, gr) in enumerate(zip(xs, gx_ref)):
         assert x.grad is not None
-        assert_close(x.grad, gr, gtol, f"{name} d/d(input) (train={train})")
-        assert rel_l2(x.grad, gr) <= (2e-2 if loose else 1e-3)
+        assert_close(x.grad, gr, tol_for(gr, gx32[i] if loose else None), f"{name} d/d(input) (train={train})")
+        assert rel_l2(x.grad, gr) <= (5e-2 if loose else 1e-3)
     named = dict(mod.named_parameters())
     checked = 0
     gmax_all = max(float(np.abs(gr).max()) for gr in g_ref.values())
@@ -123,7 +130,7 @@ def test_gradients_match_cpu_autograd(name, train):
             # subtraction): both sides hold only summation noise -- bound it relative to the real gradients
             assert float(p.grad.abs().max()) <= (5e-3 if loose else 1e-3) * gmax_all, pk
         else:
-            assert_close(p.grad, gr, gtol, f"{name} d/d({pk}) (train={train})")
+            assert_close(p.grad, gr, tol_for(gr, g32[k] if loose else None), f"{name} d/d({pk}) (train={train})")
         checked += 1
     assert checked == len(named)
 

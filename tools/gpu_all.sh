@@ -5,5 +5,16 @@ mkdir -p gpurun_out
 timeout 1500 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest -m gpu rc=$? $(tail -n 1 gpurun_out/pytest_gpu.log)"
 grep -E "^(FAILED|E  )" gpurun_out/pytest_gpu.log | cut -c1-200 | head
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-MODES="tf32 tf32x3" bash tools/gpu_bench.sh 2>&1 | grep -E "fps|smaat_" | grep -v "^#" 
+timeout 900 python bench.py > gpurun_out/bench_default.log 2>gpurun_out/bench_default.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_default.log').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','n_gpus','gpu_launches','clocks')})
+print('e2e', d['e2e']['value'], 'alt', d['alt_mode'])
+print('roofline', {k:d['roofline'][k] for k in ('kernel','achieved','frac','ms_per_step')})
+print('depthwise_roofline', {k:d['depthwise_roofline'][k] for k in ('kernel','achieved','frac','ms_per_step')})
+print('cpu_baseline', d['cpu_baseline'])
+for k,v in d['kernels'].items(): print(f"   {k:26s} n={v['launches_per_step']:3d} {v['ms_per_step']:7.3f} ms ({100*v['frac_hbm']:5.1f}% hbm) {v['tflops']:6.1f} TF")
+PY
 timeout 600 python bench_train.py --steps 5 --warmup 2 2>&1 | tail -1
+timeout 600 python bench_train.py --steps 5 --warmup 2 --mode tf32 2>&1 | tail -1
