@@ -184,47 +184,61 @@ __global__ void __launch_bounds__(256) cbam_reduce_kernel(const float* __restric
 }
 
 // ---- spatial gate: conv kxk (2->1) + affine + sigmoid ------------------------------------------------
-constexpr int GT_W = 32, GT_H = 16;
+// 32 x 32 output tile per CTA; one thread -> 4 consecutive pixels of one row.  Each (channel, tap row) needs a
+// 10-float segment of the staged tile: 2 LDS.128 + 1 LDS.64 feed 28 FMAs (10.5 shared loads per output
+// instead of 98); row pitch 40 floats keeps the 128-bit loads aligned and conflict-free per quarter-warp.
+constexpr int GT_W = 32, GT_H = 32, GT_P = 40;
 template <int KS>
 __global__ void __launch_bounds__(256) cbam_gate_kernel(const float* __restrict__ pooled, const float* __restrict__ wsp,
                                                         const float* __restrict__ bn_affine, float* __restrict__ sa,
                                                         float* __restrict__ raw, int H, int W) {
   constexpr int R = KS / 2;
-  constexpr int SW = GT_W + 2 * R, SH = GT_H + 2 * R;
-  __shared__ float t[2][SH][SW + 1];
+  constexpr int SH = GT_H + 2 * R;
+  __shared__ __align__(16) float t[2][SH][GT_P];  // column c holds global x = x0 - 4 + c (4-float left margin >= R)
   __shared__ float wk[2 * KS * KS];
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H;
   const int tid = threadIdx.x;
   if (tid < 2 * KS * KS) wk[tid] = __ldg(wsp + tid);
   const float* pb = pooled + (int64_t)b * 2 * H * W;
-  for (int i = tid; i < 2 * SH * SW; i += 256) {
-    const int ch = i / (SH * SW);
-    const int r = (i / SW) % SH, c = i % SW;
-    const int gy = y0 - R + r, gx = x0 - R + c;
+  for (int i = tid; i < 2 * SH * GT_P; i += 256) {
+    const int ch = i / (SH * GT_P);
+    const int r = (i / GT_P) % SH, c = i % GT_P;
+    const int gy = y0 - R + r, gx = x0 - 4 + c;
     float v = 0.f;
     if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(pb + ((int64_t)ch * H + gy) * W + gx);
     t[ch][r][c] = v;
   }
   __syncthreads();
-  const int tx = tid & 31, ty = tid >> 5;  // 32 x 8, two rows per thread
+  const int tx = tid & 7, ty = tid >> 3;  // 8 quads x 32 rows
   const float a_s = bn_affine ? __ldg(bn_affine) : 1.f;
   const float a_t = bn_affine ? __ldg(bn_affine + 1) : 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int oy = ty + half * 8;
-    const int gy = y0 + oy, gx = x0 + tx;
-    float acc = 0.f;
+  for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch)
+    for (int dy = 0; dy < KS; ++dy) {
+      // outputs x0+4tx+j (j<4) with taps dx read smem columns 4tx + 4 - R + j + dx: a 4+KS-1 <= 10 float window
+      const float* rowp = &t[ch][ty + dy][4 * tx];
+      const float4 v0 = *reinterpret_cast<const float4*>(rowp);
+      const float4 v1 = *reinterpret_cast<const float4*>(rowp + 4);
+      const float4 v2 = *reinterpret_cast<const float4*>(rowp + 8);
+      const float seg[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
 #pragma unroll
-      for (int dy = 0; dy < KS; ++dy)
+      for (int dx = 0; dx < KS; ++dx) {
+        const float wv = wk[(ch * KS + dy) * KS + dx];
 #pragma unroll
-        for (int dx = 0; dx < KS; ++dx) acc = fmaf(wk[(ch * KS + dy) * KS + dx], t[ch][oy + dy][tx + dx], acc);
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(wv, seg[4 - R + j + dx], acc[j]);
+      }
+    }
+  const int gy = y0 + ty;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int gx = x0 + 4 * tx + j;
     if (gy < H && gx < W) {
       const int64_t o = ((int64_t)b * H + gy) * W + gx;
-      if (raw) raw[o] = acc;
-      sa[o] = sigmoidf_acc(fmaf(acc, a_s, a_t));
+      if (raw) raw[o] = acc[j];
+      sa[o] = sigmoidf_acc(fmaf(acc[j], a_s, a_t));
     }
   }
 }

@@ -319,7 +319,7 @@ int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const flo
   SMAAT_REQUIRE(pw1x1_tc_eligible(x, w, w_lo, K, Cout, P), "pw1x1(tc): needs P %% 4 == 0, K %% 4 == 0 and 16-byte aligned x/w");
   SMAAT_REQUIRE(!x3 || w_lo, "pw1x1(tc): TF32X3 needs w_lo (see smaat_split_tf32)");
   SMAAT_REQUIRE(Cout <= 512 || (!scale && !shift), "pw1x1(tc): Cout=%d > 512 with an epilogue affine (smem staging holds 512 channels)", Cout);
-  const int n_tile = (Cout > 128 && !x3) ? 256 : (Cout > 64 ? 128 : 64);
+  const int n_tile = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
 
   CUtensorMap mx, mw, mwl;
   {
@@ -348,6 +348,7 @@ int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const flo
 
   // one persistent CTA per SM: the smem ring takes ~192 KB of the 227 KB
   if (x3) {
+    if (n_tile == 256) return launch_tc<256, 2, true>(mx, mw, mwl, p, B, st);  // activations split once per 256 channels
     if (n_tile == 128) return launch_tc<128, 3, true>(mx, mw, mwl, p, B, st);
     return launch_tc<64, 4, true>(mx, mw, mwl, p, B, st);
   }
