@@ -56,6 +56,16 @@ __global__ void __launch_bounds__(256) upsample2x_pad_kernel(const float* __rest
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[r][i] = __ldg(rp + ci[i]);
   }
+  // horizontal pass once per source row (same association as torch: w_x0*v0 + w_x1*v1), then the vertical blend
+  float hrow[3][4];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a0 = sel3(ix0[j], v[r][0], v[r][1], v[r][2], v[r][3]);
+      const float a1 = sel3(ix0[j] + 1, v[r][0], v[r][1], v[r][2], v[r][3]);
+      hrow[r][j] = (1.f - lx[j]) * a0 + lx[j] * a1;
+    }
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
     const int oy = oy0 + rr;
@@ -66,18 +76,10 @@ __global__ void __launch_bounds__(256) upsample2x_pad_kernel(const float* __rest
       const float sy = ry * (float)uy;
       const int y0 = min((int)sy, H - 1);
       const float ly = sy - (float)y0;
-      const int r0 = min(max(y0 - ya, 0), 1);  // y0 - ya is 0 or 1; row r0+1 holds min(y0+1, H-1)
+      const bool r0 = (y0 - ya) >= 1;  // y0 - ya is 0 or 1; the row below holds min(y0+1, H-1)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (xin[j]) {
-          const float t00 = sel3(ix0[j], r0 ? v[1][0] : v[0][0], r0 ? v[1][1] : v[0][1], r0 ? v[1][2] : v[0][2], r0 ? v[1][3] : v[0][3]);
-          const float t01 = sel3(ix0[j] + 1, r0 ? v[1][0] : v[0][0], r0 ? v[1][1] : v[0][1], r0 ? v[1][2] : v[0][2], r0 ? v[1][3] : v[0][3]);
-          const float t10 = sel3(ix0[j], r0 ? v[2][0] : v[1][0], r0 ? v[2][1] : v[1][1], r0 ? v[2][2] : v[1][2], r0 ? v[2][3] : v[1][3]);
-          const float t11 = sel3(ix0[j] + 1, r0 ? v[2][0] : v[1][0], r0 ? v[2][1] : v[1][1], r0 ? v[2][2] : v[1][2], r0 ? v[2][3] : v[1][3]);
-          // same association as torch's upsample_bilinear2d: w_y0*(w_x0*v00 + w_x1*v01) + w_y1*(...)
-          o[j] = (1.f - ly) * ((1.f - lx[j]) * t00 + lx[j] * t01) + ly * ((1.f - lx[j]) * t10 + lx[j] * t11);
-        }
-      }
+      for (int j = 0; j < 4; ++j)
+        if (xin[j]) o[j] = (1.f - ly) * (r0 ? hrow[1][j] : hrow[0][j]) + ly * (r0 ? hrow[2][j] : hrow[1][j]);
     }
     float* d = dst + (int64_t)rr * Wo;
     if (VEC) {
