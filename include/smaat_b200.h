@@ -206,6 +206,18 @@ int smaat_cbam_mlp_bwd(const float* avg, const float* mx, const float* w1, const
                        int B, int C, int hidden, void* stream);
 int smaat_cbam_pool_bwd(const float* x, const float* davg, const float* dmx, float* dx, int64_t N, int P, void* stream);
 
+/* ---- loss + metric bookkeeping of one training/validation step, one pass, no host sync ------------
+ * Replaces UNetBase.loss_func (models/regression_lightning.py:57-65) and PrecipitationMetrics.update
+ * (metric/precipitation_metrics.py:37-95).  pred/target: n floats.  batch_acc: double[8], overwritten:
+ *   [0] sum (p-y)^2  [1] sum (p*f-y*f)^2 (f = factor if denormalize else 1)  [2] number of NaNs in p or y
+ *   [3] TN [4] FP [5] FN [6] TP of ((x*f)*12 > threshold)  [7] n
+ * dpred (nullable): 2*(p-y)*grad_scale, the gradient of sum((p-y)^2)*grad_scale (grad_scale = 1/B).
+ * smaat_metrics_commit adds one batch to totals (double[9]: total_loss, total_loss_denorm, total_samples,
+ * total_pixels, TN, FP, FN, TP, skipped batches) on the device, skipping NaN batches like the reference (:46-48). */
+int smaat_mse_metrics_fwd(const float* pred, const float* target, int64_t n, float factor, float threshold,
+                          int denormalize, double* batch_acc, float* dpred, float grad_scale, void* stream);
+int smaat_metrics_commit(const double* batch_acc, double* totals, int batch_size, int denormalize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@ reference's own classes (``patch_reference``), and the functional kernel wrapper
 All arithmetic runs in ``libsmaat_b200.so`` (C ABI: ``include/smaat_b200.h``).
 """
 from . import _lib, ops  # noqa: F401
+from .metrics import PrecipitationMetrics, loss_func, step_loss  # noqa: F401
 from .model import SmaAt_UNet  # noqa: F401
 from .modules import (CBAM, ChannelAttention, DepthwiseSeparableConv, DoubleConvDS, DownDS, OutConv,  # noqa: F401
                       SpatialAttention, UpDS)
@@ -13,4 +14,4 @@ from .ops import get_pointwise_mode, set_fused_dsconv, set_pointwise_mode  # noq
 from .patch import patch_reference  # noqa: F401
 
 __all__ = ["SmaAt_UNet", "CBAM", "ChannelAttention", "SpatialAttention", "DepthwiseSeparableConv", "DoubleConvDS",
-           "DownDS", "UpDS", "OutConv", "patch_reference", "set_pointwise_mode", "get_pointwise_mode", "ops"]
+           "DownDS", "UpDS", "OutConv", "patch_reference", "PrecipitationMetrics", "loss_func", "step_loss", "set_pointwise_mode", "get_pointwise_mode", "ops"]

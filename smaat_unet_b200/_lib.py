@@ -54,6 +54,8 @@ SIGNATURES = {
     "smaat_cbam_bwd_main": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "smaat_cbam_mlp_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "smaat_cbam_pool_bwd": [_p, _p, _p, _p, _l, _i, _p],
+    "smaat_mse_metrics_fwd": [_p, _p, _l, _f, _f, _i, _p, _p, _f, _p],
+    "smaat_metrics_commit": [_p, _p, _i, _i, _p],
 }
 _SPECIAL = {
     "smaat_abi_version": ([], _i),

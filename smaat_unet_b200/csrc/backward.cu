@@ -362,6 +362,11 @@ __global__ void __launch_bounds__(256) outconv_bwd_weight_kernel(const float* __
 }  // namespace smaat
 
 namespace smaat {
+bool bn_bwd_v4_ok(const void* dy, const void* z, const void* dz, int P);
+int bn_act_bwd_reduce_v4_launch(const float* dy, const float* z, const float* scale, const float* shift, double* sums, int B, int C,
+                                int P, int act, cudaStream_t st);
+int bn_act_bwd_apply_v4_launch(const float* dy, const float* z, const float* scale, const float* shift, const float* a, const float* b,
+                               const float* cc, float* dz, int B, int C, int P, int act, cudaStream_t st);
 int dw3x3_bwd_input_tiled_launch(const float* dd, const float* w, float* dx0, int C0, int64_t bs0, float* dx1, int C1, int64_t bs1,
                                  int B, int H, int W, int k, cudaStream_t st);
 int dw3x3_bwd_weight_tiled_launch(const float* dd, const float* x0, int C0, int64_t bs0, const float* x1, int C1, int64_t bs1,
@@ -386,6 +391,7 @@ static inline int pick_chunks(int64_t n, int C) {
 extern "C" int smaat_bn_act_bwd_reduce(const float* dy, const float* z, const float* scale, const float* shift, double* sums, int B,
                                        int C, int P, int act, void* stream) {
   SMAAT_REQUIRE(dy && z && sums && B > 0 && C > 0 && P > 0 && C <= 65535, "bn_act_bwd_reduce: bad arguments");
+  if (bn_bwd_v4_ok(dy, z, nullptr, P)) return bn_act_bwd_reduce_v4_launch(dy, z, scale, shift, sums, B, C, P, act, (cudaStream_t)stream);
   const int chunks = pick_chunks((int64_t)B * P, C);
   bn_act_bwd_reduce_kernel<<<dim3(chunks, C), 256, 0, (cudaStream_t)stream>>>(dy, z, scale, shift, sums, B, C, P, act, chunks);
   SMAAT_LAUNCH_CHECK("smaat_bn_act_bwd_reduce");
@@ -404,6 +410,8 @@ extern "C" int smaat_bn_bwd_coeffs(const double* sums, double count, const float
 extern "C" int smaat_bn_act_bwd_apply(const float* dy, const float* z, const float* scale, const float* shift, const float* a,
                                       const float* b, const float* cc, float* dz, int B, int C, int P, int act, void* stream) {
   SMAAT_REQUIRE(dy && z && a && b && cc && dz && B > 0 && C > 0 && P > 0, "bn_act_bwd_apply: bad arguments");
+  if (bn_bwd_v4_ok(dy, z, dz, P))
+    return bn_act_bwd_apply_v4_launch(dy, z, scale, shift, a, b, cc, dz, B, C, P, act, (cudaStream_t)stream);
   unsigned gy = grid1d(P, 256, 4);
   if (gy > 65535u) gy = 65535u;
   dim3 grid(B * C, gy);

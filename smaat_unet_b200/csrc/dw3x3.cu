@@ -222,6 +222,8 @@ static void pick_tile(int H, int W, int* TW, int* TH, int* RH) {
   *RH = rh;
 }
 
+void dw_pick_tile(int H, int W, int* TW, int* TH, int* RH) { pick_tile(H, W, TW, TH, RH); }  // shared with dw3x3_bwd.cu
+
 template <int K, int RH, bool USE_TMA, bool PRO, bool VEC>
 static int launch_dw(const CUtensorMap& m0, const CUtensorMap& m1, const DwParams& p, int threads, size_t smem,
                      int64_t grid, cudaStream_t st) {

@@ -134,8 +134,313 @@ __global__ void __launch_bounds__(256) dw3x3_bwd_weight_tiled(const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA variants (W % 4 == 0, k in {1,2}): same structure as the forward kernel (dw3x3.cu) -- the halo
+// tile arrives by one bulk tensor copy per plane (out-of-bounds zero fill = padding), each thread walks
+// an RH-row strip of 4 columns with a 3-row register window, 128-bit global accesses.
+//   input : K gradient planes -> 1 dx plane, flipped taps.      bytes = 4*B*P*Cin*(k+1)
+//   weight: 1 input plane (TMA) x K gradient planes (LDG.128) -> 10*K partial sums per thread.
+// ---------------------------------------------------------------------------------------------
+void dw_pick_tile(int H, int W, int* TW, int* TH, int* RH);   // dw3x3.cu
+
+struct DwbParams {
+  const float* g;          // dd [B][Cin*k][H][W]
+  const float* w;
+  float* dx0; float* dx1;
+  int C0, C1;
+  int64_t bs0, bs1;
+  const float* in_scale; const float* in_shift;
+  float* dw; float* db;
+  int H, W;
+  int TW, TH, BW, BH, plane_floats;
+  int tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void load_row6(float* wl, const float* src) {
+  const float4 a = *reinterpret_cast<const float4*>(src + 1);
+  wl[0] = src[0]; wl[1] = a.x; wl[2] = a.y; wl[3] = a.z; wl[4] = a.w; wl[5] = src[5];
+}
+
+template <int K, int RH>
+__global__ void __launch_bounds__(256) dw3x3_bwd_input_tma(const __grid_constant__ CUtensorMap mapg, const DwbParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);   // [K][plane_floats]
+  __shared__ __align__(8) uint64_t bar;
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int tile_id = blockIdx.x % tiles, plane = blockIdx.x / tiles;
+  const int Cin = p.C0 + p.C1;
+  const int b = plane / Cin, c = plane - b * Cin;
+  const int ty = tile_id / p.tiles_x, tx = tile_id - ty * p.tiles_x;
+  const int x0 = tx * p.TW, y0 = ty * p.TH;
+  const int tid = threadIdx.x, BW = p.BW;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(&bar, (uint32_t)(K * BW * p.BH * sizeof(float)));
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) tma_load_4d(tile + kk * p.plane_floats, &mapg, &bar, x0 - 4, y0 - 1, c * K + kk, b);
+  }
+  float wr[K][9];   // flipped taps: dx[i,j] = sum w[dy][dx] * dd[i+1-dy][j+1-dx]
+#pragma unroll
+  for (int kk = 0; kk < K; ++kk)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[kk][t] = __ldg(p.w + (int64_t)(c * K + kk) * 9 + 8 - t);
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  const int P = p.H * p.W;
+  float* dst0 = (c < p.C0) ? p.dx0 + (int64_t)b * p.bs0 + (int64_t)c * P : p.dx1 + (int64_t)b * p.bs1 + (int64_t)(c - p.C0) * P;
+  const int nsx = p.TW >> 2, nsy = p.TH / RH;
+  for (int s = tid; s < nsx * nsy; s += blockDim.x) {
+    const int sy = s / nsx, sx = s - sy * nsx;
+    const int col = sx << 2, row0 = sy * RH;
+    const int gx = x0 + col;
+    if (gx >= p.W || y0 + row0 >= p.H) continue;
+    float win[K][3][6];
+    const float* trow = tile + row0 * BW + col + 3;
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) load_row6(win[kk][r], trow + kk * p.plane_floats + r * BW);
+#pragma unroll
+    for (int i = 0; i < RH; ++i) {
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) load_row6(win[kk][(i + 2) % 3], trow + kk * p.plane_floats + (i + 2) * BW);
+      const int gy = y0 + row0 + i;
+      if (gy < p.H) {
+        float o4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < K; ++kk) {
+            const float* r0 = win[kk][i % 3];
+            const float* r1 = win[kk][(i + 1) % 3];
+            const float* r2 = win[kk][(i + 2) % 3];
+            a = fmaf(wr[kk][0], r0[j], a); a = fmaf(wr[kk][1], r0[j + 1], a); a = fmaf(wr[kk][2], r0[j + 2], a);
+            a = fmaf(wr[kk][3], r1[j], a); a = fmaf(wr[kk][4], r1[j + 1], a); a = fmaf(wr[kk][5], r1[j + 2], a);
+            a = fmaf(wr[kk][6], r2[j], a); a = fmaf(wr[kk][7], r2[j + 1], a); a = fmaf(wr[kk][8], r2[j + 2], a);
+          }
+          o4[j] = a;
+        }
+        *reinterpret_cast<float4*>(dst0 + (int64_t)gy * p.W + gx) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+  }
+}
+
+template <int K, int RH, bool PRO>
+__global__ void __launch_bounds__(256) dw3x3_bwd_weight_tma(const __grid_constant__ CUtensorMap map0,
+                                                            const __grid_constant__ CUtensorMap map1, const DwbParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);   // [BH][BW] input halo tile
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float red[K * 10][8];
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int tile_id = blockIdx.x % tiles, plane = blockIdx.x / tiles;
+  const int Cin = p.C0 + p.C1;
+  const int b = plane / Cin, c = plane - b * Cin;
+  const int ty = tile_id / p.tiles_x, tx = tile_id - ty * p.tiles_x;
+  const int x0 = tx * p.TW, y0 = ty * p.TH;
+  const int tid = threadIdx.x, BW = p.BW, BH = p.BH;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(&bar, (uint32_t)(BW * BH * sizeof(float)));
+    if (c < p.C0) tma_load_4d(tile, &map0, &bar, x0 - 4, y0 - 1, c, b);
+    else tma_load_4d(tile, &map1, &bar, x0 - 4, y0 - 1, c - p.C0, b);
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  if (PRO) {  // relu(scale*x+shift) of the producer's BatchNorm on the staged tile; padding stays zero
+    const float s = __ldg(p.in_scale + c), t = __ldg(p.in_shift + c);
+    for (int i = tid; i < BW * BH; i += blockDim.x) {
+      const int r = i / BW, cc = i - r * BW;
+      const int gy = y0 - 1 + r, gx = x0 - 4 + cc;
+      const bool inb = (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W);
+      tile[i] = inb ? fmaxf(fmaf(tile[i], s, t), 0.f) : 0.f;
+    }
+    __syncthreads();
+  }
+  float acc[K][10];
+#pragma unroll
+  for (int kk = 0; kk < K; ++kk)
+#pragma unroll
+    for (int q = 0; q < 10; ++q) acc[kk][q] = 0.f;
+  const int P = p.H * p.W;
+  const float* g = p.g + ((int64_t)b * Cin + c) * K * P;
+  const int nsx = p.TW >> 2, nsy = p.TH / RH;
+  for (int s = tid; s < nsx * nsy; s += blockDim.x) {
+    const int sy = s / nsx, sx = s - sy * nsx;
+    const int col = sx << 2, row0 = sy * RH;
+    const int gx = x0 + col;
+    if (gx >= p.W || y0 + row0 >= p.H) continue;
+    float win[3][6];
+    const float* trow = tile + row0 * BW + col + 3;
+    load_row6(win[0], trow);
+    load_row6(win[1], trow + BW);
+#pragma unroll
+    for (int i = 0; i < RH; ++i) {
+      load_row6(win[(i + 2) % 3], trow + (i + 2) * BW);
+      const int gy = y0 + row0 + i;
+      if (gy < p.H) {
+        const float* r0 = win[i % 3];
+        const float* r1 = win[(i + 1) % 3];
+        const float* r2 = win[(i + 2) % 3];
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + (int64_t)kk * P + (int64_t)gy * p.W + gx));
+          const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[kk][0] = fmaf(gv[j], r0[j], acc[kk][0]); acc[kk][1] = fmaf(gv[j], r0[j + 1], acc[kk][1]);
+            acc[kk][2] = fmaf(gv[j], r0[j + 2], acc[kk][2]);
+            acc[kk][3] = fmaf(gv[j], r1[j], acc[kk][3]); acc[kk][4] = fmaf(gv[j], r1[j + 1], acc[kk][4]);
+            acc[kk][5] = fmaf(gv[j], r1[j + 2], acc[kk][5]);
+            acc[kk][6] = fmaf(gv[j], r2[j], acc[kk][6]); acc[kk][7] = fmaf(gv[j], r2[j + 1], acc[kk][7]);
+            acc[kk][8] = fmaf(gv[j], r2[j + 2], acc[kk][8]);
+            acc[kk][9] += gv[j];
+          }
+        }
+      }
+    }
+  }
+  const int lane = tid & 31, wp = tid >> 5;
+#pragma unroll
+  for (int kk = 0; kk < K; ++kk)
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+      const float v = warp_sum(acc[kk][q]);
+      if (lane == 0) red[kk * 10 + q][wp] = v;
+    }
+  __syncthreads();
+  if (tid < K * 10) {
+    const int nw = (blockDim.x + 31) >> 5;
+    float v = 0.f;
+    for (int i = 0; i < nw; ++i) v += red[tid][i];
+    const int kk = tid / 10, q = tid - kk * 10;
+    const int o = c * K + kk;
+    if (q < 9) atomicAdd(p.dw + (int64_t)o * 9 + q, v);
+    else if (p.db) atomicAdd(p.db + o, v);
+  }
+}
+
+static bool dwb_tma_geometry(int H, int W, DwbParams* p, int* rh, int* threads) {
+  if (W % 4 != 0) return false;
+  dw_pick_tile(H, W, &p->TW, &p->TH, rh);
+  p->BW = p->TW + 8;
+  p->BH = p->TH + 2;
+  if (p->BW > 256 || p->BH > 256) return false;
+  p->plane_floats = (p->BW * p->BH + 31) / 32 * 32;   // 128-byte aligned plane pitch in shared memory
+  p->tiles_x = ceil_div(W, p->TW);
+  p->tiles_y = ceil_div(H, p->TH);
+  p->H = H; p->W = W;
+  const int nstrips = (p->TW / 4) * (p->TH / *rh);
+  *threads = ((nstrips < 256 ? nstrips : 256) + 31) / 32 * 32;
+  return true;
+}
+
+template <typename Kern>
+static int dwb_set_smem(Kern kern, size_t smem, const char* what) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e));
+  }
+  return SMAAT_OK;
+}
+
+template <int K, int RH>
+static int launch_dwb_input(const CUtensorMap& mg, const DwbParams& p, int64_t grid, int threads, cudaStream_t st) {
+  const size_t smem = (size_t)K * p.plane_floats * sizeof(float);
+  auto kern = dw3x3_bwd_input_tma<K, RH>;
+  if (int r = dwb_set_smem(kern, smem, "dw3x3_bwd_input")) return r;
+  kern<<<(unsigned)grid, threads, smem, st>>>(mg, p);
+  SMAAT_LAUNCH_CHECK("smaat_dw3x3_bwd_input");
+  return SMAAT_OK;
+}
+
+template <int K, int RH, bool PRO>
+static int launch_dwb_weight(const CUtensorMap& m0, const CUtensorMap& m1, const DwbParams& p, int64_t grid, int threads,
+                             cudaStream_t st) {
+  const size_t smem = (size_t)p.plane_floats * sizeof(float);
+  auto kern = dw3x3_bwd_weight_tma<K, RH, PRO>;
+  if (int r = dwb_set_smem(kern, smem, "dw3x3_bwd_weight")) return r;
+  kern<<<(unsigned)grid, threads, smem, st>>>(m0, m1, p);
+  SMAAT_LAUNCH_CHECK("smaat_dw3x3_bwd_weight");
+  return SMAAT_OK;
+}
+
+// returns 1 when the TMA variant is not applicable (caller falls back), else SMAAT_OK / error
+static int dwb_input_try_tma(const float* dd, const float* w, float* dx0, int C0, int64_t bs0, float* dx1, int C1, int64_t bs1,
+                             int B, int H, int W, int k, cudaStream_t st) {
+  DwbParams p;
+  memset(&p, 0, sizeof(p));
+  int rh, threads;
+  if (!(k == 1 || k == 2) || !dwb_tma_geometry(H, W, &p, &rh, &threads)) return 1;
+  if (!aligned16(dd) || !aligned16(dx0) || bs0 % 4 != 0 || (C1 > 0 && (!aligned16(dx1) || bs1 % 4 != 0))) return 1;
+  const int Cin = C0 + C1;
+  p.g = dd; p.w = w; p.dx0 = dx0; p.dx1 = dx1; p.C0 = C0; p.C1 = C1; p.bs0 = bs0; p.bs1 = bs1;
+  CUtensorMap mg;
+  memset(&mg, 0, sizeof(mg));
+  const uint32_t box[4] = {(uint32_t)p.BW, (uint32_t)p.BH, 1u, 1u};
+  const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)Cin * k, (uint64_t)B};
+  const uint64_t str[4] = {0, (uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)Cin * k * H * W * 4};
+  if (int r = make_tmap_f32(&mg, dd, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, "dw3x3_bwd_input(dd)")) return r;
+  const int64_t grid = (int64_t)B * Cin * p.tiles_x * p.tiles_y;
+  SMAAT_REQUIRE(grid < (1ll << 31), "dw3x3_bwd_input: grid too large");
+  if (k == 1) return rh == 8 ? launch_dwb_input<1, 8>(mg, p, grid, threads, st) : launch_dwb_input<1, 4>(mg, p, grid, threads, st);
+  return rh == 8 ? launch_dwb_input<2, 8>(mg, p, grid, threads, st) : launch_dwb_input<2, 4>(mg, p, grid, threads, st);
+}
+
+static int dwb_weight_try_tma(const float* dd, const float* x0, int C0, int64_t bs0, const float* x1, int C1, int64_t bs1,
+                              const float* in_scale, const float* in_shift, float* dw, float* db, int B, int H, int W, int k,
+                              cudaStream_t st) {
+  DwbParams p;
+  memset(&p, 0, sizeof(p));
+  int rh, threads;
+  if (!(k == 1 || k == 2) || !dwb_tma_geometry(H, W, &p, &rh, &threads)) return 1;
+  if (!aligned16(dd) || !aligned16(x0) || bs0 % 4 != 0 || (C1 > 0 && (!aligned16(x1) || bs1 % 4 != 0))) return 1;
+  p.g = dd; p.C0 = C0; p.C1 = C1; p.bs0 = bs0; p.bs1 = bs1; p.in_scale = in_scale; p.in_shift = in_shift; p.dw = dw; p.db = db;
+  CUtensorMap m0, m1;
+  memset(&m0, 0, sizeof(m0));
+  memset(&m1, 0, sizeof(m1));
+  const uint32_t box[4] = {(uint32_t)p.BW, (uint32_t)p.BH, 1u, 1u};
+  {
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C0, (uint64_t)B};
+    const uint64_t str[4] = {0, (uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)bs0 * 4};
+    if (int r = make_tmap_f32(&m0, x0, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, "dw3x3_bwd_weight(x0)")) return r;
+  }
+  if (C1 > 0) {
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C1, (uint64_t)B};
+    const uint64_t str[4] = {0, (uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)bs1 * 4};
+    if (int r = make_tmap_f32(&m1, x1, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, "dw3x3_bwd_weight(x1)")) return r;
+  } else {
+    m1 = m0;
+  }
+  const int64_t grid = (int64_t)B * (C0 + C1) * p.tiles_x * p.tiles_y;
+  SMAAT_REQUIRE(grid < (1ll << 31), "dw3x3_bwd_weight: grid too large");
+  const bool pro = in_scale != nullptr;
+#define SMAAT_DWB_W(KK, RR) \
+  (pro ? launch_dwb_weight<KK, RR, true>(m0, m1, p, grid, threads, st) : launch_dwb_weight<KK, RR, false>(m0, m1, p, grid, threads, st))
+  if (k == 1) return rh == 8 ? SMAAT_DWB_W(1, 8) : SMAAT_DWB_W(1, 4);
+  return rh == 8 ? SMAAT_DWB_W(2, 8) : SMAAT_DWB_W(2, 4);
+#undef SMAAT_DWB_W
+}
+
 int dw3x3_bwd_input_tiled_launch(const float* dd, const float* w, float* dx0, int C0, int64_t bs0, float* dx1, int C1, int64_t bs1,
                                  int B, int H, int W, int k, cudaStream_t st) {
+  {
+    const int r = dwb_input_try_tma(dd, w, dx0, C0, bs0, dx1, C1, bs1, B, H, W, k, st);
+    if (r != 1) return r;
+  }
   const int TW = pick_tw(W);
   const int tiles_x = ceil_div(W, TW), tiles_y = ceil_div(H, DB_TH);
   const int64_t grid = (int64_t)B * (C0 + C1) * tiles_x * tiles_y;
@@ -149,6 +454,10 @@ int dw3x3_bwd_input_tiled_launch(const float* dd, const float* w, float* dx0, in
 int dw3x3_bwd_weight_tiled_launch(const float* dd, const float* x0, int C0, int64_t bs0, const float* x1, int C1, int64_t bs1,
                                   const float* in_scale, const float* in_shift, float* dw, float* db, int B, int H, int W, int k,
                                   cudaStream_t st) {
+  {
+    const int r = dwb_weight_try_tma(dd, x0, C0, bs0, x1, C1, bs1, in_scale, in_shift, dw, db, B, H, W, k, st);
+    if (r != 1) return r;
+  }
   const int TW = pick_tw(W);
   const int tiles_x = ceil_div(W, TW), tiles_y = ceil_div(H, DB_TH);
   const int64_t grid = (int64_t)B * (C0 + C1) * tiles_x * tiles_y;

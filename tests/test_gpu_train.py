@@ -164,3 +164,55 @@ def test_training_step_reduces_loss_and_matches_cpu_one_step():
         p0 = TP.smaat_unet_forward(torch.from_numpy(xs_np[0]), sd, True)
     l0 = float(torch.nn.functional.mse_loss(p0.squeeze(1), torch.from_numpy(tgt), reduction="sum") / x.shape[0])
     assert abs(losses[0] - l0) <= 1e-3 * abs(l0)
+
+
+# B, C0, C1, H, W, k, prologue  (W % 4 == 0 and k <= 2 take the TMA kernels, the rest the LDS-tiled ones)
+DW_BWD_CASES = [
+    (2, 5, 0, 9, 11, 1, False),
+    (2, 6, 0, 12, 8, 2, True),
+    (1, 4, 0, 7, 5, 3, False),
+    (2, 3, 5, 16, 20, 2, False),
+    (1, 8, 0, 18, 18, 2, True),
+    (2, 4, 0, 36, 36, 2, True),
+    (1, 3, 2, 72, 72, 1, False),
+    (1, 2, 2, 144, 144, 2, True),
+    (1, 3, 0, 288, 288, 2, False),
+    (1, 2, 0, 100, 148, 2, True),
+]
+
+
+@pytest.mark.parametrize("case", DW_BWD_CASES)
+def test_dw3x3_backward_kernels_match_cpu_autograd(case):
+    """smaat_dw3x3_bwd_input / _bwd_weight vs float64 autograd of conv2d(groups=Cin) (reference layers.py:38-44)."""
+    from smaat_unet_b200 import functional as Fn
+    B, C0, C1, H, W, k, pro = case
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + W + k)
+    Cin = C0 + C1
+    x = torch.randn(B, Cin, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(Cin * k, 1, 3, 3, generator=g, dtype=torch.float64)
+    dd = torch.randn(B, Cin * k, H, W, generator=g, dtype=torch.float64)
+    sc = torch.rand(Cin, generator=g, dtype=torch.float64) + 0.5
+    sh = torch.randn(Cin, generator=g, dtype=torch.float64) * 0.3
+    a = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    b = torch.zeros(Cin * k, dtype=torch.float64, requires_grad=True)
+    inp = torch.relu(a * sc[None, :, None, None] + sh[None, :, None, None]) if pro else a
+    y = torch.nn.functional.conv2d(inp, wr, b, padding=1, groups=Cin)
+    y.backward(dd)
+    # the kernels return d(loss)/d(conv input); with the prologue that is the gradient w.r.t. relu(BN(x))
+    if pro:
+        a2 = inp.detach().clone().requires_grad_(True)
+        torch.nn.functional.conv2d(a2, w, None, padding=1, groups=Cin).backward(dd)
+        want_dx = a2.grad
+    else:
+        want_dx = a.grad
+    f32 = lambda t: t.to(torch.float32).to(dev()).contiguous()
+    x0 = f32(x[:, :C0])
+    x1 = f32(x[:, C0:]) if C1 else None
+    dW = torch.zeros(Cin * k, 1, 3, 3, device=dev())
+    db = torch.zeros(Cin * k, device=dev())
+    dx0, dx1 = Fn.dw_bwd(f32(dd), f32(w), x0, x1, f32(sc) if pro else None, f32(sh) if pro else None, k, dW, db)
+    got_dx = torch.cat([dx0, dx1], 1) if C1 else dx0
+    assert_close(got_dx.cpu().numpy(), want_dx.numpy(), 2e-5, f"dw3x3_bwd_input {case}")
+    assert_close(dW.cpu().numpy(), wr.grad.numpy(), 1e-4, f"dw3x3_bwd_weight {case}")
+    assert_close(db.cpu().numpy(), b.grad.numpy(), 1e-4, f"dw3x3_bwd_bias {case}")
