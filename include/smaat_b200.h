@@ -164,12 +164,13 @@ int smaat_outconv_fwd(const float* x, const float* w, const float* bias, float* 
  * BatchNorm(+ReLU) backward = reduce -> coeffs -> apply:
  *   reduce: sums[c] += sum dA, sums[C+c] += sum dA*z                       (fp64)
  *   coeffs: dgamma += invstd*(S2 - mean*S1), dbeta += S1; per-channel a,b,cc with dz = a*dA + b*z + cc
- *           (train: batch-statistics terms; eval (train=0): dz = gamma*invstd*dA)
+ *           (train: batch-statistics terms; eval (train=0): dz = gamma*invstd*dA); dz_sum (nullable) += sum_{b,p} dz
+ *           per channel, i.e. the bias gradient of the conv that produced z, from the sums alone (0 with batch statistics)
  *   apply : dz[b,c,p] = a[c]*dA + b[c]*z + cc[c] */
 int smaat_bn_act_bwd_reduce(const float* dy, const float* z, const float* scale, const float* shift, double* sums,
                             int B, int C, int P, int act, void* stream);
 int smaat_bn_bwd_coeffs(const double* sums, double count, const float* gamma, const float* mean, const float* invstd, int train,
-                        float* a, float* b, float* cc, float* dgamma, float* dbeta, int C, void* stream);
+                        float* a, float* b, float* cc, float* dgamma, float* dbeta, float* dz_sum, int C, void* stream);
 int smaat_bn_act_bwd_apply(const float* dy, const float* z, const float* scale, const float* shift,
                            const float* a, const float* b, const float* cc, float* dz, int B, int C, int P, int act, void* stream);
 
@@ -195,16 +196,21 @@ int smaat_upsample2x_pad_bwd(const float* dy, int64_t dy_bstride, float* dx, int
 int smaat_outconv_bwd(const float* dy, const float* x, const float* w, float* dx, float* dW, float* db,
                       int B, int Cin, int ncls, int P, void* stream);
 
-/* CBAM backward (see cbam_bwd.cu for the chain): */
-int smaat_cbam_bwd_gate_in(const float* g, const float* x, const float* sc, const float* sa, float* dpre, int B, int C, int P, void* stream);
+/* CBAM backward (see cbam_bwd.cu for the chain): gate_in -> [BN(1) backward] -> gate_bwd -> dsc -> mlp_bwd -> dx.
+ * amax: (B, P) int32 channel argmax of x*sc written by gate_in; pkey: (B*C) uint64, zeroed by the caller, receives the
+ * packed plane argmax of x in dsc and is consumed by dx; dsc (B, C) is accumulated into (caller zeroes it). */
+int smaat_cbam_bwd_gate_in(const float* g, const float* x, const float* sc, const float* sa, float* dpre, int* amax,
+                           int B, int C, int P, void* stream);
 int smaat_cbam_gate_bwd(const float* draw, const float* pooled, const float* wsp, float* dpooled, float* dW,
                         int B, int H, int W, int ks, void* stream);
-int smaat_cbam_bwd_main(const float* g, const float* x, const float* sc, const float* sa, const float* dpooled,
-                        float* dx, float* dsc, int B, int C, int P, void* stream);
+int smaat_cbam_bwd_dsc(const float* g, const float* x, const float* sa, const float* dpooled, const int* amax, float* dsc,
+                       unsigned long long* pkey, int B, int C, int P, void* stream);
 int smaat_cbam_mlp_bwd(const float* avg, const float* mx, const float* w1, const float* b1, const float* w2, const float* sc,
                        const float* dsc, float* dw1, float* db1, float* dw2, float* db2, float* davg, float* dmx,
                        int B, int C, int hidden, void* stream);
-int smaat_cbam_pool_bwd(const float* x, const float* davg, const float* dmx, float* dx, int64_t N, int P, void* stream);
+int smaat_cbam_bwd_dx(const float* g, const float* sc, const float* sa, const float* dpooled, const int* amax,
+                      const float* davg, const float* dmx, const unsigned long long* pkey, float* dx,
+                      int B, int C, int P, void* stream);
 
 /* ---- loss + metric bookkeeping of one training/validation step, one pass, no host sync ------------
  * Replaces UNetBase.loss_func (models/regression_lightning.py:57-65) and PrecipitationMetrics.update

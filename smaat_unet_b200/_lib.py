@@ -39,7 +39,7 @@ SIGNATURES = {
     "smaat_outconv_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     # ---- backward
     "smaat_bn_act_bwd_reduce": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
-    "smaat_bn_bwd_coeffs": [_p, C.c_double, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p],
+    "smaat_bn_bwd_coeffs": [_p, C.c_double, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p],
     "smaat_bn_act_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "smaat_dw3x3_bwd_input": [_p, _p, _p, _i, _l, _p, _i, _l, _i, _i, _i, _i, _p],
     "smaat_dw3x3_bwd_weight": [_p, _p, _i, _l, _p, _i, _l, _p, _p, _p, _p, _i, _i, _i, _i, _p],
@@ -49,11 +49,11 @@ SIGNATURES = {
     "smaat_maxpool2_bwd": [_p, _p, _p, _l, _i, _i, _p],
     "smaat_upsample2x_pad_bwd": [_p, _l, _p, _i, _i, _i, _i, _i, _i, _p],
     "smaat_outconv_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
-    "smaat_cbam_bwd_gate_in": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "smaat_cbam_bwd_gate_in": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "smaat_cbam_gate_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
-    "smaat_cbam_bwd_main": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "smaat_cbam_bwd_dsc": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "smaat_cbam_bwd_dx": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "smaat_cbam_mlp_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
-    "smaat_cbam_pool_bwd": [_p, _p, _p, _p, _l, _i, _p],
     "smaat_mse_metrics_fwd": [_p, _p, _l, _f, _f, _i, _p, _p, _f, _p],
     "smaat_metrics_commit": [_p, _p, _i, _i, _p],
 }

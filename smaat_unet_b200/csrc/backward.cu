@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const float* __r
 __global__ void bn_bwd_coeffs_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
                                      const float* __restrict__ mean, const float* __restrict__ invstd, int train,
                                      float* __restrict__ a, float* __restrict__ b, float* __restrict__ cc,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dz_sum, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double S1 = sums[c], S2 = sums[C + c];
@@ -60,6 +60,9 @@ __global__ void bn_bwd_coeffs_kernel(const double* __restrict__ sums, double cou
   if (dgamma) dgamma[c] += (float)dg;
   if (dbeta) dbeta[c] += (float)S1;
   const double sc = g * is;
+  // sum_{b,p} dz (= the bias gradient of the conv that produced z): a*S1 + b*n*mean + n*cc, which is identically 0 with
+  // batch statistics and a*S1 with running statistics -- no extra pass over dz
+  if (dz_sum && !train) dz_sum[c] += (float)(sc * S1);
   a[c] = (float)sc;
   if (train) {
     const double c1 = S1 / count, c2 = dg / count;
@@ -284,32 +287,130 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// bilinear x2 (align_corners) + pad backward: scatter with fp32 atomics into a zeroed dx
+// bilinear x2 (align_corners) + pad backward, as a gather (no atomics, no memset): source row t receives from
+// the upsampled rows u in [2t-2, 2t+3] (src = u*(n-1)/(2n-1) lies in [u/2-1/2, u/2]), likewise for columns.
+// Separable: phase 1 reduces each gradient row horizontally into shared memory (6 taps per source column),
+// phase 2 reduces vertically (6 taps).  The weights repeat the forward's fp32 index arithmetic (upsample.cu),
+// so this is the exact adjoint of smaat_upsample2x_pad_fwd.
 // ---------------------------------------------------------------------------------------------
+constexpr int UB_TY = 16, UB_TX = 64, UB_ROWS = 2 * UB_TY + 4;
+
+__device__ __forceinline__ float up_adj_weight(int u, int t, int n, float r) {
+  if (u < 0 || u >= 2 * n) return 0.f;
+  const float s = r * (float)u;
+  const int i0 = min((int)s, n - 1), i1 = min(i0 + 1, n - 1);
+  const float l = s - (float)i0;
+  return (i0 == t ? 1.f - l : 0.f) + (i1 == t ? l : 0.f);
+}
+
 __global__ void __launch_bounds__(256) upsample2x_pad_bwd_kernel(const float* __restrict__ dy, int64_t dy_bstride,
                                                                  float* __restrict__ dx, int C, int H, int W, int Ho, int Wo,
-                                                                 int pad_t, int pad_l, float ry, float rx) {
+                                                                 int pad_t, int pad_l, float ry, float rx, int tiles_x) {
+  __shared__ float hs[UB_ROWS][UB_TX + 1];
+  __shared__ float wys[UB_TY][6];
   const int c = blockIdx.y, b = blockIdx.z;
-  const float* g = dy + (int64_t)b * dy_bstride + (int64_t)c * Ho * Wo;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int y0 = ty * UB_TY, x0 = tx * UB_TX;
+  const float* g = dy + (int64_t)b * dy_bstride + (int64_t)c * Ho * Wo + (int64_t)pad_t * Wo + pad_l;
+  const int col = threadIdx.x & (UB_TX - 1), rgrp = threadIdx.x / UB_TX;   // 4 row groups
+  const int x = min(x0 + col, W - 1);   // columns past the edge recompute the last one (never stored)
+  const int u0 = 2 * x - 2;
+  // out-of-range taps get weight 0 and a clamped (valid) address: no predicates in the row loop
+  float wx[6];
+  int ox[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    wx[i] = up_adj_weight(u0 + i, x, W, rx);
+    ox[i] = min(max(u0 + i, 0), 2 * W - 1);
+  }
+  if (threadIdx.x < UB_TY * 6) {
+    const int yy = threadIdx.x / 6, i = threadIdx.x - yy * 6;
+    const int y = y0 + yy;
+    wys[yy][i] = (y < H) ? up_adj_weight(2 * y - 2 + i, y, H, ry) : 0.f;
+  }
+  const int r0 = 2 * y0 - 2;   // first upsampled row this tile needs
+#pragma unroll 3
+  for (int r = rgrp; r < UB_ROWS; r += 256 / UB_TX) {
+    const int uy = min(max(r0 + r, 0), 2 * H - 1);   // rows outside the image only meet zero vertical weights
+    const float* row = g + (int64_t)uy * Wo;
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a = fmaf(wx[i], __ldg(row + ox[i]), a);
+    hs[r][col] = a;
+  }
+  __syncthreads();
+  if (x0 + col >= W) return;
   float* dst = dx + ((int64_t)b * C + c) * H * W;
-  const int total = 2 * H * 2 * W;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int uy = i / (2 * W), ux = i - uy * (2 * W);
-    const float gv = __ldg(g + (int64_t)(uy + pad_t) * Wo + ux + pad_l);
-    const float sy = ry * uy, sx = rx * ux;
-    const int y0 = min((int)sy, H - 1), x0 = min((int)sx, W - 1);
-    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-    const float ly = sy - y0, lx = sx - x0;
-    atomicAdd(dst + (int64_t)y0 * W + x0, gv * (1.f - ly) * (1.f - lx));
-    atomicAdd(dst + (int64_t)y0 * W + x1, gv * (1.f - ly) * lx);
-    atomicAdd(dst + (int64_t)y1 * W + x0, gv * ly * (1.f - lx));
-    atomicAdd(dst + (int64_t)y1 * W + x1, gv * ly * lx);
+#pragma unroll
+  for (int yy = rgrp; yy < UB_TY; yy += 256 / UB_TX) {
+    const int y = y0 + yy;
+    if (y >= H) break;
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a = fmaf(wys[yy][i], hs[2 * yy + i][col], a);
+    dst[(int64_t)y * W + x] = a;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // OutConv backward (ncls small)
 // ---------------------------------------------------------------------------------------------
+// 128-bit variants (P % 4 == 0): the input gradient streams dy once per 4 pixels and writes every channel; the weight
+// gradient is one CTA per (b, c) plane slice (no per-element index division), merged with fp32 atomics.
+__global__ void __launch_bounds__(256) outconv_bwd_input_v4(const float* __restrict__ dy, const float* __restrict__ w,
+                                                            float* __restrict__ dx, int Cin, int ncls, int P4) {
+  const int b = blockIdx.y;
+  const float4* g4 = reinterpret_cast<const float4*>(dy) + (int64_t)b * ncls * P4;
+  float4* o4 = reinterpret_cast<float4*>(dx) + (int64_t)b * Cin * P4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += gridDim.x * blockDim.x) {
+    if (ncls == 1) {
+      const float4 g = __ldg(g4 + i);
+      for (int c = 0; c < Cin; ++c) {
+        const float wv = __ldg(w + c);
+        o4[(int64_t)c * P4 + i] = make_float4(wv * g.x, wv * g.y, wv * g.z, wv * g.w);
+      }
+    } else {
+      for (int c = 0; c < Cin; ++c) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < ncls; ++j) {
+          const float wv = __ldg(w + (int64_t)j * Cin + c);
+          const float4 g = __ldg(g4 + (int64_t)j * P4 + i);
+          a.x = fmaf(wv, g.x, a.x); a.y = fmaf(wv, g.y, a.y); a.z = fmaf(wv, g.z, a.z); a.w = fmaf(wv, g.w, a.w);
+        }
+        o4[(int64_t)c * P4 + i] = a;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) outconv_bwd_weight_v4(const float* __restrict__ dy, const float* __restrict__ x,
+                                                             float* __restrict__ dW, float* __restrict__ db, int Cin, int ncls,
+                                                             int P4) {
+  const int plane = blockIdx.x, b = plane / Cin, c = plane - b * Cin;
+  const float4* x4 = reinterpret_cast<const float4*>(x) + (int64_t)plane * P4;
+  __shared__ float red[2][8];
+  for (int j = 0; j < ncls; ++j) {
+    const float4* g4 = reinterpret_cast<const float4*>(dy) + ((int64_t)b * ncls + j) * P4;
+    float a = 0.f, sg = 0.f;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P4; i += gridDim.y * blockDim.x) {
+      const float4 g = __ldg(g4 + i), xv = __ldg(x4 + i);
+      a += (g.x * xv.x + g.y * xv.y) + (g.z * xv.z + g.w * xv.w);
+      sg += (g.x + g.y) + (g.z + g.w);
+    }
+    a = warp_sum(a);
+    sg = warp_sum(sg);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = sg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float v = 0.f, u = 0.f;
+      for (int i = 0; i < 8; ++i) { v += red[0][i]; u += red[1][i]; }
+      atomicAdd(dW + (int64_t)j * Cin + c, v);
+      if (c == 0 && db) atomicAdd(db + j, u);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) outconv_bwd_input_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                                 float* __restrict__ dx, int Cin, int ncls, int P) {
   const int c = blockIdx.y, b = blockIdx.z;
@@ -399,10 +500,11 @@ extern "C" int smaat_bn_act_bwd_reduce(const float* dy, const float* z, const fl
 }
 
 extern "C" int smaat_bn_bwd_coeffs(const double* sums, double count, const float* gamma, const float* mean, const float* invstd,
-                                   int train, float* a, float* b, float* cc, float* dgamma, float* dbeta, int C, void* stream) {
+                                   int train, float* a, float* b, float* cc, float* dgamma, float* dbeta, float* dz_sum, int C,
+                                   void* stream) {
   SMAAT_REQUIRE(sums && mean && invstd && a && b && cc && C > 0 && count > 0, "bn_bwd_coeffs: bad arguments");
   bn_bwd_coeffs_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, count, gamma, mean, invstd, train, a, b, cc, dgamma,
-                                                                           dbeta, C);
+                                                                           dbeta, dz_sum, C);
   SMAAT_LAUNCH_CHECK("smaat_bn_bwd_coeffs");
   return SMAAT_OK;
 }
@@ -491,10 +593,9 @@ extern "C" int smaat_upsample2x_pad_bwd(const float* dy, int64_t dy_bstride, flo
   const int pad_t = (Ho - 2 * H) / 2, pad_l = (Wo - 2 * W) / 2;
   const float ry = (2 * H > 1) ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
   const float rx = (2 * W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
-  cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)B * C * H * W * sizeof(float), (cudaStream_t)stream);
-  if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "upsample2x_bwd: memset: %s", cudaGetErrorString(e));
-  dim3 grid(grid1d((int64_t)4 * H * W, 256, 4), C, B);
-  upsample2x_pad_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, dy_bstride, dx, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx);
+  const int tiles_x = ceil_div(W, UB_TX), tiles_y = ceil_div(H, UB_TY);
+  dim3 grid(tiles_x * tiles_y, C, B);
+  upsample2x_pad_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, dy_bstride, dx, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx, tiles_x);
   SMAAT_LAUNCH_CHECK("smaat_upsample2x_pad_bwd");
   return SMAAT_OK;
 }
@@ -504,6 +605,23 @@ extern "C" int smaat_outconv_bwd(const float* dy, const float* x, const float* w
   SMAAT_REQUIRE(dy && x && w && B > 0 && Cin > 0 && ncls > 0 && P > 0, "outconv_bwd: bad arguments");
   SMAAT_REQUIRE(Cin <= 65535 && B <= 65535, "outconv_bwd: Cin/B too large");
   cudaStream_t st = (cudaStream_t)stream;
+  const bool v4 = (P % 4 == 0) && aligned16(dy) && aligned16(x) && (!dx || aligned16(dx));
+  if (v4) {
+    const int P4 = P / 4;
+    if (dx) {
+      unsigned gx = (unsigned)ceil_div(P4, 256);
+      outconv_bwd_input_v4<<<dim3(gx, B), 256, 0, st>>>(dy, w, dx, Cin, ncls, P4);
+      SMAAT_LAUNCH_CHECK("smaat_outconv_bwd(input)");
+    }
+    if (dW) {
+      int slices = ceil_div(P4, 256 * 8);
+      if (slices > 65535) slices = 65535;
+      SMAAT_REQUIRE((int64_t)B * Cin < (1ll << 31), "outconv_bwd: too many planes");
+      outconv_bwd_weight_v4<<<dim3((unsigned)(B * Cin), (unsigned)slices), 256, 0, st>>>(dy, x, dW, db, Cin, ncls, P4);
+      SMAAT_LAUNCH_CHECK("smaat_outconv_bwd(weight)");
+    }
+    return SMAAT_OK;
+  }
   if (dx) {
     dim3 grid(grid1d(P, 256, 4), Cin, B);
     outconv_bwd_input_kernel<<<grid, 256, 0, st>>>(dy, w, dx, Cin, ncls, P);

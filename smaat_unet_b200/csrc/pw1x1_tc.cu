@@ -53,7 +53,8 @@ struct PwTcCfg {
   static constexpr int OFF_BLO = OFF_B + B_BYTES;  // X3 only
   static constexpr int BAR_BYTES = 512;
   static constexpr int AFF_N = 512;                                      // per-channel epilogue affine staged in smem
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 2 * AFF_N * 4 + 1024;  // + alignment slack
+  static constexpr int SACC_BYTES = 4 * 2 * N_TILE * 8;                  // per-epilogue-warp fp64 BatchNorm partial sums
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 2 * AFF_N * 4 + SACC_BYTES + 1024;  // + alignment slack
   static constexpr uint32_t TX_BYTES = A_BYTES + (X3 ? 2 : 1) * B_BYTES;
   static constexpr int THREADS = X3 ? 320 : 192;
   static constexpr int TMEM_COLS = 2 * N_TILE;  // two accumulator stages
@@ -182,6 +183,22 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
     // ===== epilogue warps 2..5: TMEM -> registers -> affine/ReLU -> coalesced NCHW stores =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const float act_lo = p.relu ? 0.f : -INFINITY;  // ReLU as a branch-free max()
+    // BatchNorm batch statistics: this warp's fp64 partial sums [2][N_TILE] live in shared memory across the CTA's
+    // tiles (lane j owns columns j, j+32, ...: no atomics, no sync) and reach HBM once per n-tile change / at the end
+    double* sacc = reinterpret_cast<double*>(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES + 2 * L::AFF_N * 4) + q * 2 * N_TILE;
+    int stat_n0 = -1;
+    if (p.stats)
+      for (int c = lane; c < 2 * N_TILE; c += 32) sacc[c] = 0.0;
+    auto flush_stats = [&](int n0f) {
+      for (int c = lane; c < N_TILE; c += 32) {
+        if (n0f + c < p.Cout) {
+          atomicAdd(p.stats + n0f + c, sacc[c]);
+          atomicAdd(p.stats + p.Cout + n0f + c, sacc[N_TILE + c]);
+        }
+        sacc[c] = 0.0;
+        sacc[N_TILE + c] = 0.0;
+      }
+    };
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       const int tn = tile % p.tiles_n;
@@ -189,6 +206,10 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
       const int tm = rest % p.tiles_m;
       const int b = rest / p.tiles_m;
       const int n0 = tn * N_TILE;
+      if (p.stats && n0 != stat_n0) {
+        if (stat_n0 >= 0) flush_stats(stat_n0);
+        stat_n0 = n0;
+      }
       const uint32_t acc = tcount & 1u;
       const uint32_t acc_ph = (tcount >> 1) & 1u;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
@@ -240,18 +261,17 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
             m2[j] = mv * mv;
             if (pvalid && j < nch) yp[(int64_t)j * p.P] = fmaxf(pre, act_lo);
           }
-          if (p.stats) {  // BatchNorm batch statistics: 31-shuffle transpose-reduce, then one fp64 atomic per channel
+          if (p.stats) {  // 31-shuffle transpose-reduce: lane j ends with the 32-pixel sum of channel c0 + j
             const float s1 = warp_transpose_sum32(m1, lane), s2 = warp_transpose_sum32(m2, lane);
-            if (lane < nch) {
-              atomicAdd(p.stats + n0 + c0 + lane, (double)s1);
-              atomicAdd(p.stats + p.Cout + n0 + c0 + lane, (double)s2);
-            }
+            sacc[c0 + lane] += (double)s1;
+            sacc[N_TILE + c0 + lane] += (double)s2;
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);  // 128 arrivals release the accumulator stage to the MMA warp
     }
+    if (p.stats && stat_n0 >= 0) flush_stats(stat_n0);
   } else if (X3) {
     // ===== warps 6..9: split the landed activations into tf32 hi (in place) and lo =====
     const int et = threadIdx.x - 192;  // 0..127

@@ -20,9 +20,13 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32_kk(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
+// A = the operand on the M side (TMEM lanes), B = the operand on the N side (TMEM columns).  Normally A = dz (Cout rows per
+// image) and B = d (K rows); for Cout <= 64 the roles are swapped so the 128-row A box is not half empty (transposed = 1:
+// D is dW^T and lanes map to consecutive dW addresses).
 struct WgParams {
   float* dW;
-  int K, Cout, P, B;
+  int K, Cout, P, B;       // K = rows of the B-side operand per image, Cout = rows of the A-side operand per image
+  int ldw, transposed;     // dW row pitch; 1 when D holds dW^T
   int chunks_per_img, total_chunks, chunks_per_split, tiles_o, tiles_c;
 };
 
@@ -132,10 +136,17 @@ __global__ void __launch_bounds__(WgCfg<N_TILE, X3>::THREADS, 1)
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, r);
         tmem_ld_wait();
         if (o < p.Cout) {
-          float* dst = p.dW + (int64_t)o * p.K + c0 + cc;
+          if (p.transposed) {   // D[o][c] = dW[c][o]: a warp's 32 lanes hit 32 consecutive floats
+            float* dst = p.dW + (int64_t)(c0 + cc) * p.ldw + o;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + cc + j < p.K) atomicAdd(dst + j, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j)
+              if (c0 + cc + j < p.K) atomicAdd(dst + (int64_t)j * p.ldw, __uint_as_float(r[j]));
+          } else {
+            float* dst = p.dW + (int64_t)o * p.ldw + c0 + cc;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + cc + j < p.K) atomicAdd(dst + j, __uint_as_float(r[j]));
+          }
         }
       }
       tc_fence_before();
@@ -200,6 +211,13 @@ bool pw1x1_wgrad_tc_eligible(const float* dz, const float* d, int K, int Cout, i
 
 int pw1x1_wgrad_tc_launch(const float* dz, const float* d, float* dW, int B, int K, int Cout, int P, bool x3, cudaStream_t st) {
   CUtensorMap mz, md;
+  const int ldw = K;
+  int transposed = 0;
+  if (Cout <= 64 && K > Cout) {   // put the longer operand on the 128-row M side
+    const float* t = dz; dz = d; d = t;
+    const int ti = K; K = Cout; Cout = ti;
+    transposed = 1;
+  }
   const int n_tile = K > 128 ? 256 : (K > 64 ? 128 : 64);
   {
     const uint64_t dims[2] = {(uint64_t)P, (uint64_t)B * Cout};
@@ -216,7 +234,7 @@ int pw1x1_wgrad_tc_launch(const float* dz, const float* d, float* dW, int B, int
     if (r) return r;
   }
   WgParams p;
-  p.dW = dW; p.K = K; p.Cout = Cout; p.P = P; p.B = B;
+  p.dW = dW; p.K = K; p.Cout = Cout; p.P = P; p.B = B; p.ldw = ldw; p.transposed = transposed;
   p.chunks_per_img = p.total_chunks = p.chunks_per_split = p.tiles_o = p.tiles_c = 0;
   if (x3) {
     if (n_tile == 256) return launch_wg<256, true>(mz, md, p, st);

@@ -91,8 +91,9 @@ def _zeros_like_param(p):
     return torch.zeros(p.shape, device=p.device, dtype=torch.float32)
 
 
-def bn_act_bwd(dy, z, scale, shift, gamma, mean, invstd, count, train, act, dgamma, dbeta):
-    """dL/dz for a = act(BN(z)) given dL/da; accumulates dgamma/dbeta (may be None)."""
+def bn_act_bwd(dy, z, scale, shift, gamma, mean, invstd, count, train, act, dgamma, dbeta, dz_sum=None):
+    """dL/dz for a = act(BN(z)) given dL/da; accumulates dgamma/dbeta (may be None) and, into ``dz_sum``, the per-channel
+    sum of dz (the bias gradient of the conv that produced z) without another pass over dz."""
     B, C, H, W = z.shape
     P = H * W
     lib = _lib.load()
@@ -103,7 +104,7 @@ def bn_act_bwd(dy, z, scale, shift, gamma, mean, invstd, count, train, act, dgam
     b = torch.empty_like(a)
     cc = torch.empty_like(a)
     _call("smaat_bn_bwd_coeffs", 64 * C, 0, lib.smaat_bn_bwd_coeffs, _ptr(sums), float(count), _ptr(gamma), _ptr(mean), _ptr(invstd),
-          int(bool(train)), _ptr(a), _ptr(b), _ptr(cc), _ptr(dgamma), _ptr(dbeta), C, _stream())
+          int(bool(train)), _ptr(a), _ptr(b), _ptr(cc), _ptr(dgamma), _ptr(dbeta), _ptr(dz_sum), C, _stream())
     dz = torch.empty_like(z)
     _call("smaat_bn_act_bwd_apply", 12 * B * C * P, 0, lib.smaat_bn_act_bwd_apply, _ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(a),
           _ptr(b), _ptr(cc), _ptr(dz), B, C, P, act, _stream())
@@ -166,13 +167,13 @@ def double_conv_bwd(mod, saved, g, need_x=True, need_x1=True):
     tr0 = bn0.training or not bn0.track_running_stats
     tr1 = bn1.training or not bn1.track_running_stats
     # second DS conv: out = relu(BN1(z1)), z1 = pw(d1) + b, d1 = dw(relu(BN0(z0)))
-    dz1 = bn_act_bwd(g, s["z1"], s["sc1"], s["sh1"], bn1.weight.detach(), s["m1"], s["i1"], n, tr1, 1, g1[4], g1[5])
-    dd1 = pw_bwd(dz1, s["d1"], ds1.pointwise.weight, g1[2], g1[3])
+    dz1 = bn_act_bwd(g, s["z1"], s["sc1"], s["sh1"], bn1.weight.detach(), s["m1"], s["i1"], n, tr1, 1, g1[4], g1[5], dz_sum=g1[3])
+    dd1 = pw_bwd(dz1, s["d1"], ds1.pointwise.weight, g1[2], None)      # bias gradient = sum dz: from the BN sums above
     da0, _ = dw_bwd(dd1, ds1.depthwise.weight, s["z0"], None, s["sc0"], s["sh0"], k, g1[0], g1[1])
     # first DS conv
-    dz0 = bn_act_bwd(da0, s["z0"], s["sc0"], s["sh0"], bn0.weight.detach(), s["m0"], s["i0"], n, tr0, 1, g0[4], g0[5])
+    dz0 = bn_act_bwd(da0, s["z0"], s["sc0"], s["sh0"], bn0.weight.detach(), s["m0"], s["i0"], n, tr0, 1, g0[4], g0[5], dz_sum=g0[3])
     need_in = need_x or (s["x1"] is not None and need_x1)
-    dd0 = pw_bwd(dz0, s["d0"], ds0.pointwise.weight, g0[2], g0[3])
+    dd0 = pw_bwd(dz0, s["d0"], ds0.pointwise.weight, g0[2], None)
     dx, dx1 = dw_bwd(dd0, ds0.depthwise.weight, s["x"], s["x1"], None, None, k, g0[0], g0[1], need_input=need_in)
     return dx, dx1, g0 + g1
 
@@ -188,8 +189,9 @@ def cbam_bwd(mod, saved, g):
     lib = _lib.load()
     g = ops._dense(g, "grad_output")
     dpre = torch.empty((B, 1, H, W), device=x.device)
-    _call("smaat_cbam_bwd_gate_in", 8 * B * C * P, 0, lib.smaat_cbam_bwd_gate_in, _ptr(g), _ptr(x), _ptr(sc), _ptr(sa), _ptr(dpre), B, C, P,
-          _stream())
+    amax = torch.empty((B, H, W), device=x.device, dtype=torch.int32)
+    _call("smaat_cbam_bwd_gate_in", 8 * B * C * P, 0, lib.smaat_cbam_bwd_gate_in, _ptr(g), _ptr(x), _ptr(sc), _ptr(sa), _ptr(dpre), _ptr(amax),
+          B, C, P, _stream())
     d_bn_w, d_bn_b = _zeros_like_param(bn.weight), _zeros_like_param(bn.bias)
     train = bn.training or not bn.track_running_stats
     draw = bn_act_bwd(dpre, s["raw"], s["g_sc"], s["g_sh"], bn.weight.detach(), s["g_m"], s["g_i"], B * P, train, 0, d_bn_w, d_bn_b)
@@ -198,17 +200,19 @@ def cbam_bwd(mod, saved, g):
     ks = sp.conv.weight.shape[-1]
     _call("smaat_cbam_gate_bwd", 16 * B * P, 0, lib.smaat_cbam_gate_bwd, _ptr(draw), _ptr(s["pooled"]), _ptr(sp.conv.weight.detach()),
           _ptr(dpooled), _ptr(d_conv), B, H, W, ks, _stream())
-    dx = torch.empty_like(x)
     dsc = torch.zeros((B, C), device=x.device)
-    _call("smaat_cbam_bwd_main", 16 * B * C * P, 0, lib.smaat_cbam_bwd_main, _ptr(g), _ptr(x), _ptr(sc), _ptr(sa), _ptr(dpooled), _ptr(dx),
-          _ptr(dsc), B, C, P, _stream())
+    pkey = torch.zeros((B, C), device=x.device, dtype=torch.int64)     # packed (value, ~index) plane argmax of x
+    _call("smaat_cbam_bwd_dsc", 8 * B * C * P, 0, lib.smaat_cbam_bwd_dsc, _ptr(g), _ptr(x), _ptr(sa), _ptr(dpooled), _ptr(amax), _ptr(dsc),
+          _ptr(pkey), B, C, P, _stream())
     dw1, db1, dw2, db2 = (_zeros_like_param(l1.weight), _zeros_like_param(l1.bias), _zeros_like_param(l2.weight), _zeros_like_param(l2.bias))
     davg = torch.empty((B, C), device=x.device)
     dmx = torch.empty_like(davg)
     _call("smaat_cbam_mlp_bwd", 32 * B * C, 0, lib.smaat_cbam_mlp_bwd, _ptr(s["avg"]), _ptr(s["mx"]), _ptr(l1.weight.detach()),
           _ptr(l1.bias.detach()), _ptr(l2.weight.detach()), _ptr(sc), _ptr(dsc), _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _ptr(davg),
           _ptr(dmx), B, C, l1.weight.shape[0], _stream())
-    _call("smaat_cbam_pool_bwd", 12 * B * C * P, 0, lib.smaat_cbam_pool_bwd, _ptr(x), _ptr(davg), _ptr(dmx), _ptr(dx), B * C, P, _stream())
+    dx = torch.empty_like(x)
+    _call("smaat_cbam_bwd_dx", 8 * B * C * P, 0, lib.smaat_cbam_bwd_dx, _ptr(g), _ptr(sc), _ptr(sa), _ptr(dpooled), _ptr(amax), _ptr(davg),
+          _ptr(dmx), _ptr(pkey), _ptr(dx), B, C, P, _stream())
     return dx, [dw1, db1, dw2, db2, d_conv, d_bn_w, d_bn_b]
 
 

@@ -206,13 +206,13 @@ def test_dw3x3_backward_kernels_match_cpu_autograd(case):
         want_dx = a2.grad
     else:
         want_dx = a.grad
-    f32 = lambda t: t.to(torch.float32).to(dev()).contiguous()
+    f32 = lambda t: t.to(torch.float32).cuda().contiguous()
     x0 = f32(x[:, :C0])
     x1 = f32(x[:, C0:]) if C1 else None
-    dW = torch.zeros(Cin * k, 1, 3, 3, device=dev())
-    db = torch.zeros(Cin * k, device=dev())
+    dW = torch.zeros(Cin * k, 1, 3, 3, device="cuda")
+    db = torch.zeros(Cin * k, device="cuda")
     dx0, dx1 = Fn.dw_bwd(f32(dd), f32(w), x0, x1, f32(sc) if pro else None, f32(sh) if pro else None, k, dW, db)
     got_dx = torch.cat([dx0, dx1], 1) if C1 else dx0
-    assert_close(got_dx.cpu().numpy(), want_dx.numpy(), 2e-5, f"dw3x3_bwd_input {case}")
-    assert_close(dW.cpu().numpy(), wr.grad.numpy(), 1e-4, f"dw3x3_bwd_weight {case}")
-    assert_close(db.cpu().numpy(), b.grad.numpy(), 1e-4, f"dw3x3_bwd_bias {case}")
+    assert_close(got_dx, want_dx.numpy(), 2e-5, f"dw3x3_bwd_input {case}")
+    assert_close(dW, wr.grad.numpy(), 1e-4, f"dw3x3_bwd_weight {case}")
+    assert_close(db, b.grad.numpy(), 1e-4, f"dw3x3_bwd_bias {case}")

@@ -19,3 +19,8 @@ tot = sum(a["ms"] for a in agg.values())
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
     print(f"{k:30s} n={a['launches']:4d} {a['ms']:8.2f} ms {100*a['ms']/tot:5.1f}%  {a['bytes']/max(a['ms'],1e-9)/1e6:7.0f} GB/s {a['flops']/max(a['ms'],1e-9)/1e9:7.1f} TF")
 print("total kernel ms", tot)
+print("--- GEMMs by shape")
+bs = prof.summary(by_shape=True)
+for k, a in sorted(bs.items(), key=lambda kv: -kv[1]["ms"]):
+    if "pw1x1" in k:
+        print(f"{k:48s} n={a['launches']:3d} {a['ms']:7.3f} ms {a['bytes']/max(a['ms'],1e-9)/1e6:7.0f} GB/s {a['flops']/max(a['ms'],1e-9)/1e9:7.1f} TF")
