@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--mode", default="tf32x3")
+    ap.add_argument("--no-graph", action="store_true")
     a = ap.parse_args()
     rank, world, local = PAR.env_rank_world()
     torch.cuda.set_device(local)
@@ -36,37 +37,30 @@ def main():
     B = a.global_batch // world if a.global_batch else a.batch
     torch.manual_seed(0)
     model = S.SmaAt_UNet(12, 1, kernels_per_layer=2).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    params = [p for p in model.parameters()]
+    from smaat_unet_b200.train import TrainSession
+    sess = TrainSession(model, B, (12, 288, 288), lr=1e-3, device=dev, use_graph=not a.no_graph)
     gen = torch.Generator().manual_seed(1 + rank)
-    x = torch.rand((B, 12, 288, 288), generator=gen).to(dev)
-    y = torch.rand((B, 288, 288), generator=gen).to(dev)
+    # a few distinct pinned host batches: every step copies its inputs host -> device (inside the timed region)
+    xs = [torch.rand((B, 12, 288, 288), generator=gen).pin_memory() for _ in range(2)]
+    ys = [torch.rand((B, 288, 288), generator=gen).pin_memory() for _ in range(2)]
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        pred = model(x)
-        loss = torch.nn.functional.mse_loss(pred.squeeze(1), y, reduction="sum") / B
-        loss.backward()
-        if world > 1:
-            PAR.allreduce_flat_([p.grad for p in params], average=True)
-        opt.step()
-        return loss
-
-    for _ in range(a.warmup):
-        loss = step()
+    for i in range(a.warmup):
+        loss = sess.step(xs[i % 2], ys[i % 2])
     PAR.barrier(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0 = S._lib.launch_count()
     e0.record()
-    for _ in range(a.steps):
-        loss = step()
+    for i in range(a.steps):
+        loss = sess.step(xs[i % 2], ys[i % 2])
     e1.record()
     PAR.barrier(dev)
     ms = PAR.reduce_max(e0.elapsed_time(e1), dev)
     if rank == 0:
-        print(json.dumps({"task": "train step fwd+bwd+Adam", "frames_per_s": world * B * a.steps / (ms * 1e-3), "ms_per_step": ms / a.steps,
-                          "n_gpus": world, "batch_per_gpu": B, "pointwise": a.mode, "final_loss": float(loss),
-                          "gpu_launches": int(S._lib.launch_count() - n0), "max_mem_GB": torch.cuda.max_memory_allocated() / 1e9}))
+        m = {k: float(v) for k, v in sess.metrics.compute().items()}
+        print(json.dumps({"task": "train step fwd+bwd+Adam (TrainSession: loss+metrics fused, h2d of the batch every step)",
+                          "frames_per_s": world * B * a.steps / (ms * 1e-3), "ms_per_step": ms / a.steps,
+                          "n_gpus": world, "batch_per_gpu": B, "pointwise": a.mode, "cuda_graph": not a.no_graph, "final_loss": float(loss),
+                          "gpu_launches_per_step": sess.launches_per_step, "metrics_mse": m["mse"],
+                          "max_mem_GB": torch.cuda.max_memory_allocated() / 1e9}))
     if world > 1:
         torch.distributed.destroy_process_group()
 

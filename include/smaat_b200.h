@@ -113,12 +113,13 @@ int smaat_bn_fold(const float* gamma, const float* beta, const float* rm, const 
  * bn_finalize: mean = s1/n, var = s2/n - mean^2 (biased), scale = gamma/sqrt(var+eps),
  *   shift = beta - mean*scale; writes mean / inv-std for the backward pass (may be NULL) and updates
  *   running_mean <- (1-m) rm + m mean, running_var <- (1-m) rv + m var*n/(n-1)  (may be NULL).
+ *   num_batches_tracked (nullable, device int64) is incremented by one, like nn.BatchNorm2d does in train mode.
  * affine_act: y[b,c,p] = act(scale[c]*x[b,c,p] + shift[c]), act 0 = none, 1 = ReLU, 2 = sigmoid
  *   (scale NULL = 1, shift NULL = 0). */
 int smaat_channel_stats(const float* x, double* stats, int B, int C, int P, void* stream);
 int smaat_bn_finalize(const double* stats, double count, const float* gamma, const float* beta, float eps, float momentum,
                       float* running_mean, float* running_var, float* scale, float* shift,
-                      float* mean_out, float* invstd_out, int C, void* stream);
+                      float* mean_out, float* invstd_out, long long* num_batches_tracked, int C, void* stream);
 int smaat_affine_act_fwd(const float* x, const float* scale, const float* shift, float* y,
                          int B, int C, int P, int act, void* stream);
 

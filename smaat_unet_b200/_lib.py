@@ -27,7 +27,7 @@ SIGNATURES = {
     "smaat_split_tf32": [_p, _p, _p, _l, _p],
     "smaat_bn_fold": [_p, _p, _p, _p, _p, _f, _p, _p, _i, _p],
     "smaat_channel_stats": [_p, _p, _i, _i, _i, _p],
-    "smaat_bn_finalize": [_p, C.c_double, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _i, _p],
+    "smaat_bn_finalize": [_p, C.c_double, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "smaat_affine_act_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "smaat_maxpool2_fwd": [_p, _p, _l, _i, _i, _p],
     "smaat_upsample2x_pad_fwd": [_p, _p, _l, _i, _i, _i, _i, _i, _i, _p],

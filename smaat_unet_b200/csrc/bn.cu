@@ -13,8 +13,10 @@ namespace smaat {
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   long long* __restrict__ num_batches_tracked, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
   if (c >= C) return;
   const double mean = stats[c] / count;
   double var = stats[C + c] / count - mean * mean;  // biased
@@ -112,10 +114,11 @@ using namespace smaat;
 
 extern "C" int smaat_bn_finalize(const double* stats, double count, const float* gamma, const float* beta, float eps,
                                  float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                                 float* mean_out, float* invstd_out, int C, void* stream) {
+                                 float* mean_out, float* invstd_out, long long* num_batches_tracked, int C, void* stream) {
   SMAAT_REQUIRE(stats && scale && shift && C > 0 && count > 0, "bn_finalize: bad arguments");
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, count, gamma, beta, eps, momentum, running_mean,
-                                                                         running_var, scale, shift, mean_out, invstd_out, C);
+                                                                         running_var, scale, shift, mean_out, invstd_out,
+                                                                         num_batches_tracked, C);
   SMAAT_LAUNCH_CHECK("smaat_bn_finalize");
   return SMAAT_OK;
 }

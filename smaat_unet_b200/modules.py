@@ -63,10 +63,12 @@ class DepthwiseSeparableConv(nn.Module):
         """(hi, lo) tf32 split of the pointwise weight, cached on the parameter's version counter."""
         w = self.pointwise.weight
         key = _versions(w)
-        if self._wsplit_key != key:
+        # while a training step is being captured into a CUDA graph the split must be part of the graph: replays see new weights
+        in_train_capture = self.training and torch.cuda.is_current_stream_capturing()
+        if in_train_capture or self._wsplit_key != key:
             with torch.no_grad():
                 self._wsplit = ops.split_tf32(w.detach().view(w.shape[0], -1))
-            self._wsplit_key = key
+            self._wsplit_key = None if in_train_capture else key
         return self._wsplit
 
     def run(self, x, x1=None, scale=None, shift=None, relu=False, in_scale=None, in_shift=None, stats=None):

@@ -246,9 +246,8 @@ def bn_finalize(stats, count, bn, save=False):
           _ptr(bn.weight.detach() if bn.weight is not None else None), _ptr(bn.bias.detach() if bn.bias is not None else None),
           float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1),
           _ptr(bn.running_mean if track else None), _ptr(bn.running_var if track else None),
-          _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), Cn, _stream())
-    if track and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+          _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
+          _ptr(bn.num_batches_tracked if (track and bn.num_batches_tracked is not None) else None), Cn, _stream())
     return (scale, shift, mean, invstd) if save else (scale, shift)
 
 

@@ -216,3 +216,35 @@ def test_dw3x3_backward_kernels_match_cpu_autograd(case):
     assert_close(got_dx, want_dx.numpy(), 2e-5, f"dw3x3_bwd_input {case}")
     assert_close(dW, wr.grad.numpy(), 1e-4, f"dw3x3_bwd_weight {case}")
     assert_close(db, b.grad.numpy(), 1e-4, f"dw3x3_bwd_bias {case}")
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_session_matches_eager_steps(use_graph):
+    """TrainSession (flat gradient bucket, fused loss+metrics, optional CUDA graphs) reproduces plain eager steps of
+    the same modules with torch's mse_loss + Adam, and leaves the caller's model untouched by its warm-up."""
+    from smaat_unet_b200.train import TrainSession
+    torch.manual_seed(3)
+    B, S_ = 2, 32
+    m1 = S.SmaAt_UNet(12, 1, kernels_per_layer=2).cuda().train()
+    m2 = S.SmaAt_UNet(12, 1, kernels_per_layer=2).cuda().train()
+    m2.load_state_dict(m1.state_dict())
+    xs = [torch.rand(B, 12, S_, S_, device="cuda") for _ in range(3)]
+    ys = [torch.rand(B, S_, S_, device="cuda") for _ in range(3)]
+    sess = TrainSession(m1, B, (12, S_, S_), lr=1e-3, use_graph=use_graph)
+    for k, v in m2.state_dict().items():                      # warm-up steps were rolled back
+        assert torch.equal(v, m1.state_dict()[k]), k
+    opt = torch.optim.Adam(m2.parameters(), lr=1e-3)
+    for x, y in zip(xs, ys):
+        l1 = float(sess.step(x, y))
+        opt.zero_grad(set_to_none=True)
+        l2 = torch.nn.functional.mse_loss(m2(x).squeeze(1), y, reduction="sum") / B
+        l2.backward()
+        opt.step()
+        assert abs(l1 - float(l2)) <= 2e-4 * abs(float(l2)), (l1, float(l2))
+    for (k, a), b in zip(m1.state_dict().items(), m2.state_dict().values()):
+        if a.dtype == torch.int64:
+            assert torch.equal(a, b), k
+        else:     # Adam moves every weight by ~lr per step whatever the gradient scale, and parameters whose true gradient is 0
+            # (biases in front of a batch-statistics BatchNorm) follow the sign of rounding noise: bound = 2 * steps * lr
+            assert (a - b).abs().max().item() <= 7e-3, k
+    assert int(sess.metrics.total_samples) == 3 * B
