@@ -187,17 +187,26 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
     // tiles (lane j owns columns j, j+32, ...: no atomics, no sync) and reach HBM once per n-tile change / at the end
     double* sacc = reinterpret_cast<double*>(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES + 2 * L::AFF_N * 4) + q * 2 * N_TILE;
     int stat_n0 = -1;
-    if (p.stats)
+    if (p.stats) {
       for (int c = lane; c < 2 * N_TILE; c += 32) sacc[c] = 0.0;
+      __syncwarp();
+    }
+    double stat_npix = 0.0;   // valid pixels this warp has accumulated since the last flush (warp-uniform)
     auto flush_stats = [&](int n0f) {
+      __syncwarp();
       for (int c = lane; c < N_TILE; c += 32) {
         if (n0f + c < p.Cout) {
-          atomicAdd(p.stats + n0f + c, sacc[c]);
-          atomicAdd(p.stats + p.Cout + n0f + c, sacc[N_TILE + c]);
+          // z = sc * acc + sh:  sum z = sc*S1 + n*sh,  sum z^2 = sc^2*S2 + 2*sc*sh*S1 + n*sh^2
+          const double sc = (double)aff[(n0f + c) & (L::AFF_N - 1)], sh = (double)aff[L::AFF_N + ((n0f + c) & (L::AFF_N - 1))];
+          const double S1 = sacc[c], S2 = sacc[N_TILE + c];
+          atomicAdd(p.stats + n0f + c, sc * S1 + stat_npix * sh);
+          atomicAdd(p.stats + p.Cout + n0f + c, sc * sc * S2 + 2.0 * sc * sh * S1 + stat_npix * sh * sh);
         }
         sacc[c] = 0.0;
         sacc[N_TILE + c] = 0.0;
       }
+      stat_npix = 0.0;
+      __syncwarp();
     };
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
@@ -241,7 +250,7 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int nch = min(32, p.Cout - (n0 + c0));  // warp-uniform
         float* yp = ypix + (int64_t)(n0 + c0) * p.P;
-        if (p.stats == nullptr && nch == 32) {
+        if (nch == 32) {
           // hot path: 5 instructions per channel (FFMA, FMNMX, 64-bit pointer bump, predicated STG), no branches
           if (pvalid) {
 #pragma unroll
@@ -252,22 +261,21 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
           }
         } else {
 #pragma unroll
-          float m1[32], m2[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float pre = fmaf(__uint_as_float(r[j]), scv[j], shv[j]);
-            const float mv = (pvalid && j < nch) ? pre : 0.f;
-            m1[j] = mv;
-            m2[j] = mv * mv;
-            if (pvalid && j < nch) yp[(int64_t)j * p.P] = fmaxf(pre, act_lo);
-          }
-          if (p.stats) {  // 31-shuffle transpose-reduce: lane j ends with the 32-pixel sum of channel c0 + j
-            const float s1 = warp_transpose_sum32(m1, lane), s2 = warp_transpose_sum32(m2, lane);
-            sacc[c0 + lane] += (double)s1;
-            sacc[N_TILE + c0 + lane] += (double)s2;
-          }
+          for (int j = 0; j < 32; ++j)
+            if (pvalid && j < nch) yp[(int64_t)j * p.P] = fmaxf(fmaf(__uint_as_float(r[j]), scv[j], shv[j]), act_lo);
+        }
+        if (p.stats) {
+          // BatchNorm batch statistics from the RAW accumulators, re-read from TMEM in fragment layout (several pixels per
+          // thread: 14 shuffles per 32 channels).  Pixels past P and channels past Cout are exact zeros (TMA zero fill),
+          // so no masks; the epilogue affine is applied analytically when the sums are flushed.
+          float s1, s2;
+          tmem_colsum32(taddr, lane, s1, s2);
+          const int col = c0 + tmem_colsum32_col(lane);
+          sacc[col] += (double)s1;
+          sacc[N_TILE + col] += (double)s2;
         }
       }
+      if (p.stats) stat_npix += (double)max(0, min(32, p.P - (tm * TC_BM + q * 32)));
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);  // 128 arrivals release the accumulator stage to the MMA warp
     }

@@ -79,6 +79,59 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Fragment-shaped TMEM read: 16 lanes x 32 columns.  Thread T gets, for i = 0..3 and e = 0,1:
+//   f[4i + e]     = lane T/4,     column 8i + 2(T%4) + e
+//   f[4i + 2 + e] = lane T/4 + 8, column 8i + 2(T%4) + e
+// (the mma m16n8 accumulator layout, repeated over 4 column groups).  Several pixels (lanes) per thread make a
+// reduction over pixels mostly register-local -- see tmem_colsum32.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&f)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(f[0]), "=r"(f[1]), "=r"(f[2]), "=r"(f[3]), "=r"(f[4]), "=r"(f[5]), "=r"(f[6]), "=r"(f[7]), "=r"(f[8]),
+        "=r"(f[9]), "=r"(f[10]), "=r"(f[11]), "=r"(f[12]), "=r"(f[13]), "=r"(f[14]), "=r"(f[15])
+      : "r"(taddr));
+}
+
+// Column sums (s1) and sums of squares (s2) over the 32 TMEM lanes of this warp's quarter for the 32 columns at
+// taddr (lane field = first lane of the quarter).  On return lane T holds the totals of column tmem_colsum32_col(T).
+// 2 fragment loads + 14 shuffles instead of a 62-shuffle register transpose.
+__device__ __forceinline__ int tmem_colsum32_col(int lane) {
+  return 8 * (((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)) + 2 * (lane & 3) + ((lane >> 2) & 1);
+}
+__device__ __forceinline__ void tmem_colsum32(uint32_t taddr, int lane, float& sum, float& sumsq) {
+  float s1[8], s2[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) s1[v] = s2[v] = 0.f;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t f[16];
+    tmem_ld_16x256b_x4(taddr + ((uint32_t)(16 * half) << 16), f);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float a = __uint_as_float(f[4 * i + e]), b = __uint_as_float(f[4 * i + 2 + e]);
+        s1[2 * i + e] += a + b;
+        s2[2 * i + e] = fmaf(a, a, fmaf(b, b, s2[2 * i + e]));
+      }
+  }
+#pragma unroll
+  for (int s = 4; s >= 1; s >>= 1) {   // lanes differing in bits 4, 3, 2 hold the other rows of the same columns
+    const int x = s * 4;
+    const bool up = (lane & x) != 0;
+#pragma unroll
+    for (int v = 0; v < s; ++v) {
+      const float k1 = up ? s1[v + s] : s1[v], d1 = up ? s1[v] : s1[v + s];
+      const float k2 = up ? s2[v + s] : s2[v], d2 = up ? s2[v] : s2[v + s];
+      s1[v] = k1 + __shfl_xor_sync(0xffffffffu, d1, x);
+      s2[v] = k2 + __shfl_xor_sync(0xffffffffu, d2, x);
+    }
+  }
+  sum = s1[0];
+  sumsq = s2[0];
+}
+
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
 // v[j] = this lane's value for channel j (32 channels).  Returns, in lane L, the sum over the 32 lanes of
