@@ -108,16 +108,7 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __grid_constant__ CUte
   if (USE_TMA) {
     __syncthreads();  // barrier init by thread 0 must be visible before anyone polls it
     mbar_wait(&bar, 0);
-    if (PRO) {  // activation on the staged tile; the zero padding must stay zero
-      const float s = __ldg(p.in_scale + c), t = __ldg(p.in_shift + c);
-      for (int i = tid; i < BW * BH; i += blockDim.x) {
-        const int r = i / BW, cc = i - r * BW;
-        const int gy = y0 - 1 + r, gx = x0 - 4 + cc;
-        const bool inb = (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W);
-        tile[i] = inb ? fmaxf(fmaf(tile[i], s, t), 0.f) : 0.f;
-      }
-      __syncthreads();
-    }
+    // PRO: relu(scale*x+shift) is applied while the register window is loaded (below); the zero padding stays zero
   } else {
     __syncthreads();
   }
@@ -145,18 +136,29 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __grid_constant__ CUte
       float win[3][6];
       // smem column of global x is x - (x0 - 4): the 4 outputs at col..col+3 read smem cols col+3..col+8
       const float* trow = tile + row0 * BW + col + 3;
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
+      // TMA path + PRO: activation on load; rows / edge columns outside the image are the conv's zero padding
+      const bool tma_pro = USE_TMA && PRO;
+      float ps = 1.f, pt = 0.f;
+      if (tma_pro) { ps = __ldg(p.in_scale + c); pt = __ldg(p.in_shift + c); }
+      const bool lpad = (gx == 0), rpad = (gx + 4 >= p.W);
+      auto load_row = [&](float* wl, int r) {   // r = tile row relative to row0 (0 .. RH+1); image row y0 + row0 + r - 1
         const float4 a = *reinterpret_cast<const float4*>(trow + r * BW + 1);
-        win[r][0] = trow[r * BW]; win[r][1] = a.x; win[r][2] = a.y; win[r][3] = a.z; win[r][4] = a.w; win[r][5] = trow[r * BW + 5];
-      }
+        wl[0] = trow[r * BW]; wl[1] = a.x; wl[2] = a.y; wl[3] = a.z; wl[4] = a.w; wl[5] = trow[r * BW + 5];
+        if (tma_pro) {
+          const int gyr = y0 + row0 + r - 1;
+          const bool rowin = (gyr >= 0) && (gyr < p.H);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const bool in = rowin && !(q == 0 && lpad) && !(q == 5 && rpad) && (q == 0 || q == 5 || gx + q - 1 < p.W);
+            wl[q] = in ? fmaxf(fmaf(wl[q], ps, pt), 0.f) : 0.f;
+          }
+        }
+      };
+#pragma unroll
+      for (int r = 0; r < 2; ++r) load_row(win[r], r);
 #pragma unroll
       for (int i = 0; i < RH; ++i) {
-        {
-          const float4 a = *reinterpret_cast<const float4*>(trow + (i + 2) * BW + 1);
-          float* wl = win[(i + 2) % 3];
-          wl[0] = trow[(i + 2) * BW]; wl[1] = a.x; wl[2] = a.y; wl[3] = a.z; wl[4] = a.w; wl[5] = trow[(i + 2) * BW + 5];
-        }
+        load_row(win[(i + 2) % 3], i + 2);
         const int gy = y0 + row0 + i;
         if (gy < p.H) {
           const float* r0 = win[i % 3];

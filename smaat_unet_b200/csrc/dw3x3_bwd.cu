@@ -260,16 +260,10 @@ __global__ void __launch_bounds__(256) dw3x3_bwd_weight_tma(const __grid_constan
   }
   __syncthreads();
   mbar_wait(&bar, 0);
-  if (PRO) {  // relu(scale*x+shift) of the producer's BatchNorm on the staged tile; padding stays zero
-    const float s = __ldg(p.in_scale + c), t = __ldg(p.in_shift + c);
-    for (int i = tid; i < BW * BH; i += blockDim.x) {
-      const int r = i / BW, cc = i - r * BW;
-      const int gy = y0 - 1 + r, gx = x0 - 4 + cc;
-      const bool inb = (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W);
-      tile[i] = inb ? fmaxf(fmaf(tile[i], s, t), 0.f) : 0.f;
-    }
-    __syncthreads();
-  }
+  // PRO: relu(scale*x+shift) of the producer's BatchNorm is applied while the register window is loaded; positions
+  // outside the image are the conv's zero padding and stay zero
+  float ps = 1.f, pt = 0.f;
+  if (PRO) { ps = __ldg(p.in_scale + c); pt = __ldg(p.in_shift + c); }
   float acc[K][10];
 #pragma unroll
   for (int kk = 0; kk < K; ++kk)
@@ -285,11 +279,24 @@ __global__ void __launch_bounds__(256) dw3x3_bwd_weight_tma(const __grid_constan
     if (gx >= p.W || y0 + row0 >= p.H) continue;
     float win[3][6];
     const float* trow = tile + row0 * BW + col + 3;
-    load_row6(win[0], trow);
-    load_row6(win[1], trow + BW);
+    const bool lpad = (gx == 0), rpad = (gx + 4 >= p.W);
+    auto load_row = [&](float* wl, int r) {   // r: tile row relative to row0; image row y0 + row0 + r - 1
+      load_row6(wl, trow + r * BW);
+      if (PRO) {
+        const int gyr = y0 + row0 + r - 1;
+        const bool rowin = (gyr >= 0) && (gyr < p.H);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const bool in = rowin && !(q == 0 && lpad) && !(q == 5 && rpad);
+          wl[q] = in ? fmaxf(fmaf(wl[q], ps, pt), 0.f) : 0.f;
+        }
+      }
+    };
+    load_row(win[0], 0);
+    load_row(win[1], 1);
 #pragma unroll
     for (int i = 0; i < RH; ++i) {
-      load_row6(win[(i + 2) % 3], trow + (i + 2) * BW);
+      load_row(win[(i + 2) % 3], i + 2);
       const int gy = y0 + row0 + i;
       if (gy < p.H) {
         const float* r0 = win[i % 3];

@@ -1,93 +1,94 @@
 // upsample.cu -- nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True) + F.pad to the skip size
 // (reference models/unet_parts_depthwise_separable.py:64,78-81), forward.
 //
-// Write-bound (output 4x the input).  One thread produces a 2-row x 4-pixel output block: with a source
-// step < 0.5 per output pixel those 8 outputs depend on at most 3 source rows x 4 source columns, which
-// are loaded once (12 loads per 8 outputs instead of 32) from a 4x smaller plane that stays in L1/L2;
-// two 128-bit stores.  grid = (row-pair x quad blocks of one plane, C, B): 32-bit index math only.
-// Index math follows torch's area_pixel_compute_source_index for align_corners=True: src = dst*(in-1)/(out-1).
+// Write-bound (output 4x the input): algorithmic bytes = 4*B*C*(H*W + Ho*Wo).  One CTA produces a 48 x 72 output tile
+// of one plane, separably, through shared memory:
+//   * the per-column / per-row source index and the two lerp weights are computed ONCE per CTA into small tables
+//     (pad rows/columns get weights 0), so the per-pixel work has no index arithmetic;
+//   * the <= 26 x 38 source patch is staged with clamped coordinates (the clamp is torch's x1 = min(x0+1, W-1));
+//   * phase 1: horizontal lerp of every staged source row at the tile's 72 output columns (2 LDS + 2 FP each);
+//   * phase 2: vertical lerp, 4 output columns per thread: 2 LDS.128 + 8 FP + one 128-bit store.
+// Index math follows torch's area_pixel_compute_source_index for align_corners=True: src = dst*(in-1)/(out-1),
+// and the blend keeps torch's association w_y0*(w_x0*v00 + w_x1*v01) + w_y1*(w_x0*v10 + w_x1*v11).
 #include "common.cuh"
 
 namespace smaat {
 
-__device__ __forceinline__ float sel3(int i, float a, float b, float c, float d) {
-  return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : d));
-}
+constexpr int UP_TY = 48, UP_TX = 72;          // output tile
+constexpr int UP_SR = 27, UP_SC = 40;          // staged source patch (rows, cols) incl. the +1 neighbours
+constexpr int UP_SP = UP_SC + 1;               // pitch
+constexpr int UP_THREADS = (UP_TX / 4) * 12;   // 18 column quads x 12 row lanes = 216
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) upsample2x_pad_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                             int64_t y_bstride, int C, int H, int W, int Ho, int Wo,
-                                                             int pad_t, int pad_l, float ry, float rx) {
-  const int wq = (Wo + 3) >> 2, hp = (Ho + 1) >> 1;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= hp * wq) return;
-  const int op = idx / wq;
-  const int oy0 = op << 1;
-  const int ox0 = (idx - op * wq) << 2;
+__global__ void __launch_bounds__(UP_THREADS) upsample2x_pad_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                    int64_t y_bstride, int C, int H, int W, int Ho, int Wo,
+                                                                    int pad_t, int pad_l, float ry, float rx, int tiles_x) {
+  __shared__ float src[UP_SR * UP_SP];
+  __shared__ __align__(16) float hs[UP_SR][UP_TX];
+  __shared__ int cidx[UP_TX], ridx[UP_TY];
+  __shared__ float cw0[UP_TX], cw1[UP_TX], rw0[UP_TY], rw1[UP_TY];
   const int c = blockIdx.y, b = blockIdx.z;
-  const float* src = x + ((int64_t)b * C + c) * H * W;
-  float* dst = y + (int64_t)b * y_bstride + ((int64_t)c * Ho + oy0) * Wo + ox0;
-
-  // source columns: xa .. xa+3 (clamped) cover every tap of the 4 output pixels
-  const int uxa = max(ox0 - pad_l, 0);
-  const int xa = min((int)(rx * (float)uxa), W - 1);
-  int ci[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) ci[i] = min(xa + i, W - 1);
-  int ix0[4];
-  float lx[4];
-  bool xin[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int ux = ox0 + j - pad_l;
-    xin[j] = (ux >= 0) && (ux < 2 * W);
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int oy_t = ty * UP_TY, ox_t = tx * UP_TX;
+  const int tid = threadIdx.x;
+  // first source column / row any output of this tile can touch
+  const int xa = min((int)(rx * (float)max(ox_t - pad_l, 0)), W - 1);
+  const int ya = min((int)(ry * (float)max(oy_t - pad_t, 0)), H - 1);
+  if (tid < UP_TX) {
+    const int ux = ox_t + tid - pad_l;
+    const bool in = (ux >= 0) && (ux < 2 * W) && (ox_t + tid < Wo);
     const float sx = rx * (float)max(ux, 0);
     const int x0 = min((int)sx, W - 1);
-    lx[j] = sx - (float)x0;
-    ix0[j] = min(max(x0 - xa, 0), 2);
+    const float lx = sx - (float)x0;
+    cidx[tid] = min(max(x0 - xa, 0), UP_SC - 2);
+    cw0[tid] = in ? 1.f - lx : 0.f;
+    cw1[tid] = in ? lx : 0.f;
+  } else if (tid < UP_TX + UP_TY) {
+    const int r = tid - UP_TX;
+    const int uy = oy_t + r - pad_t;
+    const bool in = (uy >= 0) && (uy < 2 * H) && (oy_t + r < Ho);
+    const float sy = ry * (float)max(uy, 0);
+    const int y0 = min((int)sy, H - 1);
+    const float ly = sy - (float)y0;
+    ridx[r] = min(max(y0 - ya, 0), UP_SR - 2);
+    rw0[r] = in ? 1.f - ly : 0.f;
+    rw1[r] = in ? ly : 0.f;
   }
-  // source rows: ya .. ya+2 (clamped) cover both output rows
-  const int uya = max(oy0 - pad_t, 0);
-  const int ya = min((int)(ry * (float)uya), H - 1);
-  float v[3][4];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const float* rp = src + (int64_t)min(ya + r, H - 1) * W;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[r][i] = __ldg(rp + ci[i]);
+  const float* plane = x + ((int64_t)b * C + c) * H * W;
+  for (int i = tid; i < UP_SR * UP_SC; i += UP_THREADS) {
+    const int r = i / UP_SC, cc = i - r * UP_SC;
+    src[r * UP_SP + cc] = __ldg(plane + (int64_t)min(ya + r, H - 1) * W + min(xa + cc, W - 1));
   }
-  // horizontal pass once per source row (same association as torch: w_x0*v0 + w_x1*v1), then the vertical blend
-  float hrow[3][4];
+  __syncthreads();
+  // phase 1: hs[r][j] = w_x0 * src[r][x0] + w_x1 * src[r][x0 + 1]
+  for (int i = tid; i < UP_SR * UP_TX; i += UP_THREADS) {
+    const int r = i / UP_TX, j = i - r * UP_TX;
+    const float* s = src + r * UP_SP + cidx[j];
+    hs[r][j] = cw0[j] * s[0] + cw1[j] * s[1];
+  }
+  __syncthreads();
+  // phase 2: out[r][4q..4q+3] = w_y0 * hs[y0][..] + w_y1 * hs[y0 + 1][..]
+  const int q = tid % (UP_TX / 4), rl = tid / (UP_TX / 4);
+  const int ox = ox_t + 4 * q;
+  if (ox >= Wo) return;
+  float* dst = y + (int64_t)b * y_bstride + (int64_t)c * Ho * Wo + ox;
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float a0 = sel3(ix0[j], v[r][0], v[r][1], v[r][2], v[r][3]);
-      const float a1 = sel3(ix0[j] + 1, v[r][0], v[r][1], v[r][2], v[r][3]);
-      hrow[r][j] = (1.f - lx[j]) * a0 + lx[j] * a1;
-    }
-#pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int oy = oy0 + rr;
+  for (int r = rl; r < UP_TY; r += 12) {
+    const int oy = oy_t + r;
     if (oy >= Ho) break;
-    const int uy = oy - pad_t;
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    if (uy >= 0 && uy < 2 * H) {
-      const float sy = ry * (float)uy;
-      const int y0 = min((int)sy, H - 1);
-      const float ly = sy - (float)y0;
-      const bool r0 = (y0 - ya) >= 1;  // y0 - ya is 0 or 1; the row below holds min(y0+1, H-1)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (xin[j]) o[j] = (1.f - ly) * (r0 ? hrow[1][j] : hrow[0][j]) + ly * (r0 ? hrow[2][j] : hrow[1][j]);
-    }
-    float* d = dst + (int64_t)rr * Wo;
+    const int y0 = ridx[r];
+    const float w0 = rw0[r], w1 = rw1[r];
+    const float4 a = *reinterpret_cast<const float4*>(&hs[y0][4 * q]);
+    const float4 bb = *reinterpret_cast<const float4*>(&hs[y0 + 1][4 * q]);
+    const float o0 = w0 * a.x + w1 * bb.x, o1 = w0 * a.y + w1 * bb.y, o2 = w0 * a.z + w1 * bb.z, o3 = w0 * a.w + w1 * bb.w;
+    float* d = dst + (int64_t)oy * Wo;
     if (VEC) {
-      *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(d) = make_float4(o0, o1, o2, o3);
     } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (ox0 + j < Wo) d[j] = o[j];
+      d[0] = o0;
+      if (ox + 1 < Wo) d[1] = o1;
+      if (ox + 2 < Wo) d[2] = o2;
+      if (ox + 3 < Wo) d[3] = o3;
     }
   }
 }
@@ -107,11 +108,14 @@ extern "C" int smaat_upsample2x_pad_fwd(const float* x, float* y, int64_t y_bstr
   const float ry = (2 * H > 1) ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
   const float rx = (2 * W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
   const bool vec = (Wo % 4 == 0) && aligned16(y) && (y_bstride % 4 == 0);
-  dim3 grid(ceil_div(ceil_div(Ho, 2) * ceil_div(Wo, 4), 256), C, B);
+  const int tiles_x = ceil_div(Wo, UP_TX), tiles_y = ceil_div(Ho, UP_TY);
+  dim3 grid(tiles_x * tiles_y, C, B);
   if (vec)
-    upsample2x_pad_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx);
+    upsample2x_pad_kernel<true><<<grid, UP_THREADS, 0, (cudaStream_t)stream>>>(x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx,
+                                                                              tiles_x);
   else
-    upsample2x_pad_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx);
+    upsample2x_pad_kernel<false><<<grid, UP_THREADS, 0, (cudaStream_t)stream>>>(x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx,
+                                                                               tiles_x);
   SMAAT_LAUNCH_CHECK("smaat_upsample2x_pad_fwd");
   return SMAAT_OK;
 }
