@@ -92,6 +92,14 @@ int smaat_dsconv_fwd(const float* x0, int C0, int64_t x0_bstride, const float* x
                      const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_w_lo,
                      const float* scale, const float* shift, float* y, int64_t y_bstride, double* stats,
                      int B, int H, int W, int k, int Cout, int relu, int mode, void* stream);
+/* The network's last two modules in one kernel: the fused DS conv above followed by OutConv(Cout -> 1 class)
+ * (models/SmaAt_UNet.py:55-56, unet_parts.py:67-73).  oc_w: (Cout), oc_b: (1) or NULL, logits: (B, 1, H, W); the
+ * Cout-channel activation is reduced in the epilogue registers (TMEM lane = pixel) and never written.  Same eligibility
+ * as smaat_dsconv_fwd. */
+int smaat_dsconv_outconv_fwd(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
+                             const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_w_lo,
+                             const float* scale, const float* shift, const float* oc_w, const float* oc_b, float* logits,
+                             int B, int H, int W, int k, int Cout, int relu, int mode, void* stream);
 
 /* 1 if this (x, w, K, Cout, P) can take the tcgen05 path (P % 4 == 0, K % 4 == 0, 16-byte aligned
  * pointers, Cout >= 8), else 0: the caller then uses SMAAT_PW_FP32_SIMT. */
@@ -145,6 +153,10 @@ int smaat_upsample2x_pad_fwd(const float* x, float* y, int64_t y_bstride,
  *         if raw != NULL the pre-BN conv output a is also written (train-mode statistics).
  * scale:  y[b,c,p] = x[b,c,p] * sc[b,c] * sa[b,p]   (layers.py:110,128) */
 int smaat_cbam_pool_fwd(const float* x, float* avg, float* mx, int64_t N, int P, void* stream);
+/* The same pools plus nn.MaxPool2d(2) of the same planes in ONE read of x (every encoder map of SmaAt-UNet feeds both
+ * cbam_l and down_l: models/SmaAt_UNet.py:42-50).  x: (N, H, W) -> avg (N), mx (N), pooled (N, H/2, W/2).
+ * SMAAT_E_UNSUPPORTED unless W % 4 == 0 and H % 2 == 0 (then run smaat_cbam_pool_fwd + smaat_maxpool2_fwd). */
+int smaat_cbam_pool_maxpool_fwd(const float* x, float* avg, float* mx, float* pooled, int64_t N, int H, int W, void* stream);
 int smaat_cbam_mlp_fwd(const float* avg, const float* mx, const float* w1, const float* b1,
                        const float* w2, const float* b2, float* sc, int B, int C, int hidden, void* stream);
 int smaat_cbam_reduce_fwd(const float* x, const float* sc, float* pooled, int B, int C, int P, void* stream);

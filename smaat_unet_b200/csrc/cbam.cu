@@ -288,9 +288,76 @@ __global__ void __launch_bounds__(256) cbam_scale_kernel(const float* __restrict
   }
 }
 
+// Global avg/max pool of a plane AND its 2x2 max-pool in the same read: in SmaAt-UNet every encoder map feeds both
+// cbam_l (ChannelAttention pools, layers.py:107-108) and down_l (MaxPool2d(2), parts_ds.py:48) -- models/SmaAt_UNet.py:42-50.
+// A thread takes the same 4 columns of rows 2i and 2i+1 (two 128-bit loads), emits 2 pooled outputs (64-bit store) and
+// folds all 8 values into the plane's sum / max.  TPP threads per plane (256: one plane per CTA; 32: 8 planes per CTA).
+template <int TPP>
+__global__ void __launch_bounds__(256) cbam_pool_maxpool_kernel(const float* __restrict__ x, float* __restrict__ avg,
+                                                                float* __restrict__ mx, float* __restrict__ pooled, int64_t N,
+                                                                int H, int W) {
+  constexpr int PPB = 256 / TPP;
+  const int sub = threadIdx.x / TPP, lane = threadIdx.x % TPP;
+  const int64_t n = (int64_t)blockIdx.x * PPB + sub;
+  const int wq = W >> 2, hp = H >> 1;
+  const int items = wq * hp;
+  float s = 0.f, m = -INFINITY;
+  if (n < N) {
+    const float4* src = reinterpret_cast<const float4*>(x + n * (int64_t)H * W);
+    float2* dst = reinterpret_cast<float2*>(pooled + n * (int64_t)hp * (W >> 1));
+#pragma unroll 2
+    for (int i = lane; i < items; i += TPP) {
+      const int rp = i / wq, q = i - rp * wq;
+      const float4 a = __ldg(src + (int64_t)(2 * rp) * wq + q), b = __ldg(src + (int64_t)(2 * rp + 1) * wq + q);
+      const float m0 = fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)), m1 = fmaxf(fmaxf(a.z, a.w), fmaxf(b.z, b.w));
+      dst[(int64_t)rp * wq + q] = make_float2(m0, m1);
+      s += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+      m = fmaxf(m, fmaxf(m0, m1));
+    }
+  }
+  s = warp_sum(s);
+  m = warp_max(m);
+  if (TPP == 32) {
+    if (lane == 0 && n < N) {
+      avg[n] = s / (float)(H * W);
+      mx[n] = m;
+    }
+  } else {
+    __shared__ float ss[8], sm[8];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { ss[w] = s; sm[w] = m; }
+    __syncthreads();
+    if (threadIdx.x == 0 && n < N) {
+      float S = 0.f, M = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { S += ss[i]; M = fmaxf(M, sm[i]); }
+      avg[n] = S / (float)(H * W);
+      mx[n] = M;
+    }
+  }
+}
+
 }  // namespace smaat
 
 using namespace smaat;
+
+/* x: (N, H, W) planes -> avg (N), mx (N), pooled (N, H/2, W/2).  Needs W % 4 == 0, H % 2 == 0 and 16-byte aligned x,
+ * 8-byte aligned pooled; SMAAT_E_UNSUPPORTED otherwise (run smaat_cbam_pool_fwd and smaat_maxpool2_fwd). */
+extern "C" int smaat_cbam_pool_maxpool_fwd(const float* x, float* avg, float* mx, float* pooled, int64_t N, int H, int W,
+                                           void* stream) {
+  SMAAT_REQUIRE(x && avg && mx && pooled && N > 0 && H > 0 && W > 0, "cbam_pool_maxpool: bad arguments");
+  if (W % 4 != 0 || H % 2 != 0 || !aligned16(x) || (reinterpret_cast<uintptr_t>(pooled) & 7u))
+    return fail(SMAAT_E_UNSUPPORTED, "cbam_pool_maxpool: needs W %% 4 == 0, even H and aligned pointers (H=%d W=%d)", H, W);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((int64_t)H * W >= 2048) {
+    SMAAT_REQUIRE(N < (1ll << 31), "cbam_pool_maxpool: too many planes");
+    cbam_pool_maxpool_kernel<256><<<(unsigned)N, 256, 0, st>>>(x, avg, mx, pooled, N, H, W);
+  } else {
+    cbam_pool_maxpool_kernel<32><<<(unsigned)ceil_div64(N, 8), 256, 0, st>>>(x, avg, mx, pooled, N, H, W);
+  }
+  SMAAT_LAUNCH_CHECK("smaat_cbam_pool_maxpool_fwd");
+  return SMAAT_OK;
+}
 
 extern "C" int smaat_cbam_pool_fwd(const float* x, float* avg, float* mx, int64_t N, int P, void* stream) {
   SMAAT_REQUIRE(x && avg && mx && N > 0 && P > 0, "cbam_pool: bad arguments");

@@ -33,6 +33,9 @@ struct DsParams {
   float* y;
   int64_t y_bstride;
   double* stats;
+  const float* oc_w;   // fused OutConv (1 class): logits = sum_c oc_w[c] * act[c] + oc_b, written instead of y
+  const float* oc_b;
+  float* oc_y;
   int C0, C1, H, W, Cout, relu, K;
   int tiles_x, tiles_y, total_tiles, nchunks;
 };
@@ -58,7 +61,7 @@ struct DsCfg {
   static constexpr int OFF_BAR = OFF_BR + BS * BST_BYTES;
   static constexpr int BAR_BYTES = 512;
   static constexpr int AFF_N = 128;
-  static constexpr int TOTAL = OFF_BAR + BAR_BYTES + 2 * AFF_N * 4 + 1024;
+  static constexpr int TOTAL = OFF_BAR + BAR_BYTES + 3 * AFF_N * 4 + 1024;   // scale | shift | OutConv weights
   static constexpr uint32_t B_TX = BST_BYTES;
   static constexpr int THREADS = 64 + 128 + 256 + 32;         // + warp 14: weight-ring loader
   static_assert(IS >= 2, "input ring");
@@ -123,6 +126,7 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
   for (int c = threadIdx.x; c < L::AFF_N; c += blockDim.x) {
     aff[c] = (c < p.Cout && p.scale) ? __ldg(p.scale + c) : 1.f;
     aff[L::AFF_N + c] = (c < p.Cout && p.shift) ? __ldg(p.shift + c) : 0.f;
+    aff[2 * L::AFF_N + c] = (c < p.Cout && p.oc_w) ? __ldg(p.oc_w + c) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -231,6 +235,7 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
       mbar_wait(&tmem_full[acc], (tcount >> 1) & 1u);
       tc_fence_after();
       float* ypix = p.y + (int64_t)b * p.y_bstride + (int64_t)gy * p.W + gx;
+      float oc_dot = 0.f;   // fused OutConv: this pixel's dot product over all Cout activations (lane = pixel)
 #pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         if (c0 >= p.Cout) break;
@@ -247,7 +252,19 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
         tmem_ld_wait();
         const int nchn = min(32, p.Cout - c0);
         float* yp = ypix + (int64_t)c0 * P;
-        if (p.stats == nullptr && nchn == 32) {
+        if (p.oc_y) {
+          // channels past Cout have zero accumulators, identity affine and zero OutConv weight: no mask needed
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(aff + 2 * L::AFF_N + c0 + 4 * j4);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * j4 + e;
+              oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(r[j]), scv[j], shv[j]), act_lo), wv[e], oc_dot);
+            }
+          }
+        } else if (p.stats == nullptr && nchn == 32) {
           if (pvalid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -275,6 +292,7 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
           }
         }
       }
+      if (p.oc_y && pvalid) p.oc_y[(int64_t)b * P + (int64_t)gy * p.W + gx] = oc_dot + (p.oc_b ? __ldg(p.oc_b) : 0.f);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
@@ -295,8 +313,18 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
         const float* in_stage = reinterpret_cast<const float*>(smem + s * L::IN_BYTES);
 #pragma unroll 1
         for (int task = t; task < CC * 8; task += 128) {
-          const int ci = task >> 3, strip = task & 7;
-          const int qc = strip % (PW / 4), rg = strip / (PW / 4);
+          // task -> (input channel ci, column quad qc, row group rg).  A quarter-warp (8 lanes: one 128-bit shared-memory
+          // wavefront) must touch 8 different 16-byte bank groups: PW = 32 -> the 8 quads of one channel row; PW = 16 ->
+          // the 4 quads of TWO channels (16 words apart in the input tile, and 2 k-rows apart = a different 32-byte-atom
+          // swizzle phase in the A operand).  Pairing the two row groups of one channel instead (rows 4 apart: 96 words in
+          // the input tile, 4 KB in the A operand) put both halves on the same banks: every LDS.128 / STS.128 2-way.
+          int ci, qc, rg;
+          if (PW == 32) {
+            ci = task >> 3; qc = task & 7; rg = 0;
+          } else {
+            qc = task & 3; ci = ((task >> 4) << 1) | ((task >> 2) & 1); rg = (task >> 3) & 1;
+          }
+          constexpr int NQ = PW / 4;
           const int c0 = qc << 2, r0 = rg << 2;
           const int gch = i * CC + ci;  // global input channel of this task
           float wr[KPL][9], br[KPL];
@@ -311,18 +339,25 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
           // smem column of patch column c (dx = -1..1) is c + 4 + dx: the 4 outputs read cols c0+3 .. c0+8
           const float* trow = in_stage + (ci * BH + r0) * BW + c0 + 3;
           float win[3][6];
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
+          // one LDS.128 per row; the two edge values come from the neighbouring quads' registers (lane -1 / +1 hold columns
+          // c0-4..c0-1 / c0+4..c0+7 of the same channel row), only the first / last quad of a patch row reads the halo
+          // column -- the 32 lanes' scalar loads would all fall on 8 banks (stride 4 words): a 4-way conflict each
+          const bool lb = (qc == 0), rb = (qc == NQ - 1);
+          const int edge = lb ? 0 : 5;
+          auto load_row = [&](float* wl, int r) {
             const float4 a = *reinterpret_cast<const float4*>(trow + r * BW + 1);
-            win[r][0] = trow[r * BW]; win[r][1] = a.x; win[r][2] = a.y; win[r][3] = a.z; win[r][4] = a.w; win[r][5] = trow[r * BW + 5];
-          }
+            float left = __shfl_up_sync(0xffffffffu, a.w, 1), right = __shfl_down_sync(0xffffffffu, a.x, 1);
+            if (lb | rb) {
+              const float e = trow[r * BW + edge];
+              if (lb) left = e; else right = e;
+            }
+            wl[0] = left; wl[1] = a.x; wl[2] = a.y; wl[3] = a.z; wl[4] = a.w; wl[5] = right;
+          };
+#pragma unroll
+          for (int r = 0; r < 2; ++r) load_row(win[r], r);
 #pragma unroll
           for (int rr = 0; rr < 4; ++rr) {
-            {
-              const float4 a = *reinterpret_cast<const float4*>(trow + (rr + 2) * BW + 1);
-              float* wl = win[(rr + 2) % 3];
-              wl[0] = trow[(rr + 2) * BW]; wl[1] = a.x; wl[2] = a.y; wl[3] = a.z; wl[4] = a.w; wl[5] = trow[(rr + 2) * BW + 5];
-            }
+            load_row(win[(rr + 2) % 3], rr + 2);
             const float* w0 = win[rr % 3];
             const float* w1 = win[(rr + 1) % 3];
             const float* w2 = win[(rr + 2) % 3];
@@ -422,16 +457,17 @@ extern "C" int smaat_dsconv_eligible(const float* x0, int C0, int64_t x0_bstride
   return ds_eligible(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, nullptr, H, W, k, Cout) ? 1 : 0;
 }
 
-extern "C" int smaat_dsconv_fwd(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
-                                const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_w_lo,
-                                const float* scale, const float* shift, float* y, int64_t y_bstride, double* stats, int B, int H,
-                                int W, int k, int Cout, int relu, int mode, void* stream) {
-  SMAAT_REQUIRE(x0 && dw_w && pw_w && y, "dsconv: null pointer");
+static int dsconv_run(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride, const float* dw_w,
+                      const float* dw_b, const float* pw_w, const float* pw_w_lo, const float* scale, const float* shift, float* y,
+                      int64_t y_bstride, double* stats, const float* oc_w, const float* oc_b, float* oc_y, int B, int H, int W,
+                      int k, int Cout, int relu, int mode, void* stream) {
+  SMAAT_REQUIRE(x0 && dw_w && pw_w && (y || oc_y), "dsconv: null pointer");
   SMAAT_REQUIRE(B > 0 && C0 > 0 && C1 >= 0 && H > 0 && W > 0 && Cout > 0, "dsconv: bad shape");
   SMAAT_REQUIRE(C1 == 0 || x1, "dsconv: C1=%d but x1 is null", C1);
   SMAAT_REQUIRE(mode == SMAAT_PW_TF32 || mode == SMAAT_PW_TF32X3, "dsconv: mode must be SMAAT_PW_TF32 or SMAAT_PW_TF32X3");
   SMAAT_REQUIRE(mode != SMAAT_PW_TF32X3 || pw_w_lo, "dsconv: TF32X3 needs pw_w_lo (see smaat_split_tf32)");
-  SMAAT_REQUIRE(y_bstride >= (int64_t)Cout * H * W, "dsconv: y batch stride too small");
+  SMAAT_REQUIRE(oc_y || y_bstride >= (int64_t)Cout * H * W, "dsconv: y batch stride too small");
+  SMAAT_REQUIRE(!oc_y || (oc_w && !stats), "dsconv+outconv: needs the OutConv weight and no batch statistics");
   if (!ds_eligible(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, pw_w_lo, H, W, k, Cout))
     return fail(SMAAT_E_UNSUPPORTED, "dsconv: shape not taken by the fused kernel (k=%d Cout=%d H=%d W=%d); use dw3x3 + pw1x1", k,
                 Cout, H, W);
@@ -472,6 +508,7 @@ extern "C" int smaat_dsconv_fwd(const float* x0, int C0, int64_t x0_bstride, con
   }
   DsParams p;
   p.dw_w = dw_w; p.dw_b = dw_b; p.scale = scale; p.shift = shift; p.y = y; p.y_bstride = y_bstride; p.stats = stats;
+  p.oc_w = oc_w; p.oc_b = oc_b; p.oc_y = oc_y;
   p.C0 = C0; p.C1 = C1; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu; p.K = K;
   p.tiles_x = p.tiles_y = p.total_tiles = p.nchunks = 0;
 
@@ -486,4 +523,25 @@ extern "C" int smaat_dsconv_fwd(const float* x0, int C0, int64_t x0_bstride, con
     else        { if (pw == 32) { DS_DISPATCH(128, 1, 32); } else { DS_DISPATCH(128, 1, 16); } }
   }
 #undef DS_DISPATCH
+}
+
+extern "C" int smaat_dsconv_fwd(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
+                                const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_w_lo,
+                                const float* scale, const float* shift, float* y, int64_t y_bstride, double* stats, int B, int H,
+                                int W, int k, int Cout, int relu, int mode, void* stream) {
+  SMAAT_REQUIRE(y, "dsconv: null output");
+  return dsconv_run(x0, C0, x0_bstride, x1, C1, x1_bstride, dw_w, dw_b, pw_w, pw_w_lo, scale, shift, y, y_bstride, stats, nullptr,
+                    nullptr, nullptr, B, H, W, k, Cout, relu, mode, stream);
+}
+
+/* The network's last two modules in one kernel: DS conv -> BN/ReLU -> OutConv(Cout -> 1) (reference models/SmaAt_UNet.py:55-56,
+ * unet_parts.py:67-73).  The Cout-channel activation never reaches HBM: each epilogue thread owns one pixel's Cout values
+ * (TMEM lane = pixel) and reduces them against oc_w.  logits: (B, 1, H, W). */
+extern "C" int smaat_dsconv_outconv_fwd(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
+                                        const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_w_lo,
+                                        const float* scale, const float* shift, const float* oc_w, const float* oc_b,
+                                        float* logits, int B, int H, int W, int k, int Cout, int relu, int mode, void* stream) {
+  SMAAT_REQUIRE(oc_w && logits, "dsconv+outconv: null pointer");
+  return dsconv_run(x0, C0, x0_bstride, x1, C1, x1_bstride, dw_w, dw_b, pw_w, pw_w_lo, scale, shift, nullptr, 0, nullptr, oc_w, oc_b,
+                    logits, B, H, W, k, Cout, relu, mode, stream);
 }

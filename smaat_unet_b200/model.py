@@ -34,11 +34,17 @@ class SmaAt_UNet(nn.Module):
         self.outc = OutConv(64, n_classes)
 
     def forward(self, x):
-        feats = [self.inc(x)]
+        f = self.inc(x)
+        att = []
         for lvl in range(1, 5):
-            feats.append(getattr(self, f"down{lvl}")(feats[-1]))   # un-attended maps feed the encoder
-        att = [getattr(self, f"cbam{lvl + 1}")(f) for lvl, f in enumerate(feats)]
+            # the un-attended map feeds both cbam_l and down_l (SmaAt_UNet.py:42-50): one read of it yields the channel
+            # gate's global pools and the 2x2 max-pool (inference; with autograd / odd shapes `pooled` is None)
+            a, pooled = getattr(self, f"cbam{lvl}")(f, with_maxpool=True)
+            att.append(a)
+            f = getattr(self, f"down{lvl}")(f, pooled=pooled)
+        att.append(self.cbam5(f))
         y = att[4]                                                  # x5Att is the decoder input
-        for i in range(4):
+        for i in range(3):
             y = getattr(self, f"up{i + 1}")(y, att[3 - i])          # attended maps are the skips
-        return self.outc(y)
+        # up4 and outc (SmaAt_UNet.py:55-56): in inference the 1x1 OutConv rides the last DS conv's epilogue
+        return self.up4(y, att[0], outconv=self.outc)

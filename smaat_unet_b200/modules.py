@@ -71,7 +71,7 @@ class DepthwiseSeparableConv(nn.Module):
             self._wsplit_key = None if in_train_capture else key
         return self._wsplit
 
-    def run(self, x, x1=None, scale=None, shift=None, relu=False, in_scale=None, in_shift=None, stats=None):
+    def run(self, x, x1=None, scale=None, shift=None, relu=False, in_scale=None, in_shift=None, stats=None, outconv=None):
         """dw -> pw with the pw epilogue y = act(scale * acc + shift).  scale/shift None => (1, pointwise.bias)."""
         self._check()
         dw_b = self.depthwise.bias.detach() if self.depthwise.bias is not None else None
@@ -82,9 +82,11 @@ class DepthwiseSeparableConv(nn.Module):
         if in_scale is None:
             # one kernel: the k*Cin-channel depthwise result never reaches HBM (where the shape allows)
             y = ops.dsconv(x, self.depthwise.weight.detach(), dw_b, self.kernels_per_layer, self.pointwise.weight.detach(),
-                           scale, shift, relu, x1=x1, mode=mode, w_split=split, stats=stats)
+                           scale, shift, relu, x1=x1, mode=mode, w_split=split, stats=stats, outconv=outconv)
             if y is not None:
                 return y
+        if outconv is not None:
+            return None      # the caller runs this conv and the OutConv separately
         d = ops.dw3x3(x, self.depthwise.weight.detach(), dw_b, self.kernels_per_layer, x1=x1, in_scale=in_scale, in_shift=in_shift)
         return ops.pw1x1(d, self.pointwise.weight.detach(), scale, shift, relu, mode=mode, w_split=split, stats=stats)
 
@@ -127,8 +129,13 @@ class DoubleConvDS(nn.Module):
             hit = self._fold[idx]
         return hit[1]
 
-    def run(self, x, x1=None):
+    def run(self, x, x1=None, outconv=None):
+        """``outconv`` (an OutConv module with one class, inference only): fold it into the last kernel's epilogue and
+        return the logits -- the block's own output is then never materialised (models/SmaAt_UNet.py:55-56)."""
         ops._req(x, "input", 4)
+        if outconv is not None:
+            y = self._run_with_outconv(x, x1, outconv)
+            return y if y is not None else outconv(self.run(x, x1))
         if _needs_grad(self, x, x1):
             from .autograd import DoubleConvDSFn
             return DoubleConvDSFn.run(self, x, x1)
@@ -140,6 +147,18 @@ class DoubleConvDS(nn.Module):
         y = self.double_conv[0].run(x, x1=x1, scale=s0, shift=t0, relu=True)
         s1, t1 = self._folded(3)
         return self.double_conv[3].run(y, scale=s1, shift=t1, relu=True)
+
+    def _run_with_outconv(self, x, x1, outconv):
+        bns = (self.double_conv[1], self.double_conv[4])
+        oc = outconv.conv
+        if (_needs_grad(self, x, x1) or _needs_grad(outconv, x) or self.training or oc.out_channels != 1
+                or any(not bn.track_running_stats or bn.running_mean is None for bn in bns)):
+            return None
+        s0, t0 = self._folded(0)
+        y = self.double_conv[0].run(x, x1=x1, scale=s0, shift=t0, relu=True)
+        s1, t1 = self._folded(3)
+        ob = oc.bias.detach() if oc.bias is not None else None
+        return self.double_conv[3].run(y, scale=s1, shift=t1, relu=True, outconv=(oc.weight.detach(), ob))
 
     def forward(self, x):
         return self.run(x)
@@ -155,12 +174,14 @@ class DownDS(nn.Module):
             DoubleConvDS(in_channels, out_channels, kernels_per_layer=kernels_per_layer),
         )
 
-    def forward(self, x):
-        if _needs_grad(self, x):
-            from .autograd import MaxPool2Fn
-            pooled = MaxPool2Fn.apply(x) if x.requires_grad else ops.maxpool2(x)
-        else:
-            pooled = ops.maxpool2(x)
+    def forward(self, x, pooled=None):
+        """``pooled``: MaxPool2d(2)(x) when the caller already has it (CBAM(..., with_maxpool=True))."""
+        if pooled is None:
+            if _needs_grad(self, x):
+                from .autograd import MaxPool2Fn
+                pooled = MaxPool2Fn.apply(x) if x.requires_grad else ops.maxpool2(x)
+            else:
+                pooled = ops.maxpool2(x)
         return self.maxpool_conv[1].run(pooled)
 
 
@@ -180,7 +201,7 @@ class UpDS(nn.Module):
             self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
             self.conv = DoubleConvDS(in_channels, out_channels, kernels_per_layer=kernels_per_layer)
 
-    def forward(self, x1, x2):
+    def forward(self, x1, x2, outconv=None):
         if not self.bilinear:
             raise NotImplementedError("UpDS(bilinear=False) (ConvTranspose2d upsampling, parts_ds.py:72-73) is not "
                                       "implemented in this build; the SmaAt-UNet configs use bilinear=True")
@@ -189,7 +210,7 @@ class UpDS(nn.Module):
             up = Upsample2xPadFn.apply(x1, x2.shape[2], x2.shape[3])
         else:
             up = ops.upsample2x_pad(x1, x2.shape[2], x2.shape[3])
-        return self.conv.run(x2, x1=up)
+        return self.conv.run(x2, x1=up, outconv=outconv)
 
 
 class OutConv(nn.Module):
@@ -228,11 +249,18 @@ class ChannelAttention(nn.Module):
             nn.Linear(input_channels // reduction_ratio, input_channels),
         )
 
-    def gate(self, x):
-        """sigmoid(MLP(avg) + MLP(max)) as a (B, C) tensor."""
-        avg, mx = ops.cbam_pool(x)
+    def gate(self, x, with_maxpool=False):
+        """sigmoid(MLP(avg) + MLP(max)) as a (B, C) tensor.  ``with_maxpool``: also return MaxPool2d(2)(x) (or None), computed
+        in the same read of x as the global pools."""
+        pooled = None
+        fused = ops.cbam_pool_maxpool(x) if with_maxpool else None
+        if fused is not None:
+            avg, mx, pooled = fused
+        else:
+            avg, mx = ops.cbam_pool(x)
         l1, l2 = self.MLP[1], self.MLP[3]
-        return ops.cbam_mlp(avg, mx, l1.weight.detach(), l1.bias.detach(), l2.weight.detach(), l2.bias.detach())
+        sc = ops.cbam_mlp(avg, mx, l1.weight.detach(), l1.bias.detach(), l2.weight.detach(), l2.bias.detach())
+        return (sc, pooled) if with_maxpool else sc
 
     def forward(self, x):
         _no_autograd(self, x)
@@ -283,13 +311,22 @@ class CBAM(nn.Module):
         self.channel_att = ChannelAttention(input_channels, reduction_ratio=reduction_ratio)
         self.spatial_att = SpatialAttention(kernel_size=kernel_size)
 
-    def forward(self, x, out=None):
+    def forward(self, x, out=None, with_maxpool=False):
+        """``with_maxpool=True`` returns (CBAM(x), MaxPool2d(2)(x) or None): the encoder's next DownDS pools the same map
+        (models/SmaAt_UNet.py:42-50), so the inference path produces it in the channel gate's read of x."""
         if _needs_grad(self, x):
             from .autograd import CBAMFn
-            return CBAMFn.run(self, x)
+            y = CBAMFn.run(self, x)
+            return (y, None) if with_maxpool else y
         if self.spatial_att.bn.training or not self.spatial_att.bn.track_running_stats:
             from . import functional as Fn       # batch statistics for the gate's BatchNorm2d(1), no tape
-            return Fn.cbam_fwd(self, ops._dense(x, "x"))[0]
-        sc = self.channel_att.gate(x)
+            y = Fn.cbam_fwd(self, ops._dense(x, "x"))[0]
+            return (y, None) if with_maxpool else y
+        pooled = None
+        if with_maxpool:
+            sc, pooled = self.channel_att.gate(x, with_maxpool=True)
+        else:
+            sc = self.channel_att.gate(x)
         sa = self.spatial_att.gate(x, sc)
-        return ops.cbam_scale(x, sc, sa, out=out)
+        y = ops.cbam_scale(x, sc, sa, out=out)
+        return (y, pooled) if with_maxpool else y

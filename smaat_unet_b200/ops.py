@@ -177,9 +177,10 @@ def set_fused_dsconv(enabled: bool) -> None:
     _fuse_ds = bool(enabled)
 
 
-def dsconv(x, dw_weight, dw_bias, k, pw_weight, scale, shift, relu, x1=None, mode=None, w_split=None, stats=None):
+def dsconv(x, dw_weight, dw_bias, k, pw_weight, scale, shift, relu, x1=None, mode=None, w_split=None, stats=None, outconv=None):
     """Fused DepthwiseSeparableConv (layers.py:47-50) + affine (+ReLU); returns None when the fused kernel
-    does not take this shape/mode (caller then runs dw3x3 + pw1x1)."""
+    does not take this shape/mode (caller then runs dw3x3 + pw1x1).  ``outconv=(weight (1, Cout[,1,1]), bias or None)``
+    appends the 1-class OutConv in the epilogue and returns the (B, 1, H, W) logits instead of the activation."""
     mode = mode or _pw_mode
     if not _fuse_ds or PW_MODES[mode] == 0:
         return None
@@ -199,8 +200,16 @@ def dsconv(x, dw_weight, dw_bias, k, pw_weight, scale, shift, relu, x1=None, mod
     if PW_MODES[mode] == 2:
         w2d, wlo = w_split if w_split is not None else split_tf32(w2d)
     dw_w = _dense(dw_weight, "depthwise.weight")
-    y = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.float32)
     Cin = C0 + C1
+    if outconv is not None:
+        ow, ob = outconv
+        assert ow.numel() == Cout and stats is None, "fused OutConv: one class over the block's Cout channels, no batch statistics"
+        logits = torch.empty((B, 1, H, W), device=x.device, dtype=torch.float32)
+        _call(f"smaat_dsconv_outconv_fwd[C{Cin}_N{Cout}_S{H}]", 4 * B * H * W * (Cin + 1) + 4 * K * Cout, 2 * B * H * W * (K * (Cout + 9) + Cout),
+              lib.smaat_dsconv_outconv_fwd, _ptr(x), C0, bs0, _ptr(x1), C1, bs1, _ptr(dw_w), _ptr(dw_bias), _ptr(w2d), _ptr(wlo), _ptr(scale),
+              _ptr(shift), _ptr(_dense(ow, "outconv.weight")), _ptr(ob), _ptr(logits), B, H, W, k, Cout, int(bool(relu)), PW_MODES[mode], _stream())
+        return logits
+    y = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.float32)
     _call(f"smaat_dsconv_fwd[C{Cin}_N{Cout}_S{H}]", 4 * B * H * W * (Cin + Cout) + 4 * K * Cout, 2 * B * H * W * K * (Cout + 9),
           lib.smaat_dsconv_fwd, _ptr(x), C0, bs0, _ptr(x1), C1, bs1, _ptr(dw_w), _ptr(dw_bias), _ptr(w2d), _ptr(wlo), _ptr(scale),
           _ptr(shift), _ptr(y), Cout * H * W, _ptr(stats), B, H, W, k, Cout, int(bool(relu)), PW_MODES[mode], _stream())
@@ -287,6 +296,20 @@ def cbam_pool(x):
     mx = torch.empty_like(avg)
     _call("smaat_cbam_pool_fwd", 4 * B * Cc * H * W, 0, _lib.load().smaat_cbam_pool_fwd, _ptr(x), _ptr(avg), _ptr(mx), B * Cc, H * W, _stream())
     return avg, mx
+
+
+def cbam_pool_maxpool(x):
+    """(avg, mx, maxpool2(x)) from one read of x, or None when the shape is not taken (odd H, W % 4 != 0)."""
+    x = _dense(x, "x")
+    B, Cc, H, W = x.shape
+    if W % 4 != 0 or H % 2 != 0:
+        return None
+    avg = torch.empty((B, Cc), device=x.device, dtype=torch.float32)
+    mx = torch.empty_like(avg)
+    pooled = torch.empty((B, Cc, H // 2, W // 2), device=x.device, dtype=torch.float32)
+    _call("smaat_cbam_pool_maxpool_fwd", 5 * B * Cc * H * W, 0, _lib.load().smaat_cbam_pool_maxpool_fwd, _ptr(x), _ptr(avg), _ptr(mx),
+          _ptr(pooled), B * Cc, H, W, _stream())
+    return avg, mx, pooled
 
 
 def cbam_mlp(avg, mx, w1, b1, w2, b2):

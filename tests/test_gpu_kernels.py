@@ -232,6 +232,29 @@ def test_dsconv_fused_matches_oracle(case, mode):
     assert_close(stats[:Cout], pre.sum(axis=(0, 2, 3)), 2e-3 if mode == "tf32" else 1e-4, "dsconv channel sums")
 
 
+@pytest.mark.parametrize("mode", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("case", [DS_CASES[1], DS_CASES[2], DS_CASES[3], DS_CASES[5]])
+def test_dsconv_with_fused_outconv_matches_oracle(case, mode):
+    """smaat_dsconv_outconv_fwd: DS conv -> BN/ReLU -> OutConv(Cout -> 1) with the activation kept in registers."""
+    B, C0, C1, H, W, k, Cout = case
+    C = C0 + C1
+    x = rnd(B, C, H, W)
+    dw_w, dw_b = rnd(k * C, 1, 3, 3), rnd(k * C)
+    pw_w = rnd(Cout, k * C, 1, 1, lo=-0.2, hi=0.2)
+    scale, shift = rnd(Cout, lo=0.5, hi=1.5), rnd(Cout)
+    ow, ob = rnd(1, Cout, 1, 1), rnd(1)
+    acc = O.pointwise1x1(O.depthwise3x3(x.astype(np.float64), dw_w, dw_b, k), pw_w, None)
+    act = np.maximum(acc * scale[None, :, None, None] + shift[None, :, None, None], 0)
+    ref = O.pointwise1x1(act, ow, ob)
+    x0 = dev(x[:, :C0])
+    x1 = dev(x[:, C0:]) if C1 else None
+    y = ops.dsconv(x0, dev(dw_w), dev(dw_b), k, dev(pw_w), dev(scale), dev(shift), True, x1=x1, mode=mode, outconv=(dev(ow), dev(ob)))
+    assert y is not None and tuple(y.shape) == (B, 1, H, W)
+    assert_close(y, ref, PW_TOL[mode], f"dsconv+outconv {mode} {case}")
+    y = ops.dsconv(x0, dev(dw_w), dev(dw_b), k, dev(pw_w), dev(scale), dev(shift), True, x1=x1, mode=mode, outconv=(dev(ow), None))
+    assert_close(y, ref - ob[0], PW_TOL[mode], f"dsconv+outconv without bias {mode} {case}")
+
+
 def test_dsconv_ineligible_shapes_fall_back():
     # Cout > 128 / tiny planes are not fused: ops.dsconv says so and the module path still gives the right answer
     assert ops.dsconv(dev(rnd(1, 16, 8, 8)), dev(rnd(32, 1, 3, 3)), None, 2, dev(rnd(256, 32, 1, 1)), None, None, False) is None
@@ -241,3 +264,16 @@ def test_dsconv_ineligible_shapes_fall_back():
     ref = O.ds_conv(x.astype(np.float64), {"m." + k_: v for k_, v in sd.items()}, "m", 2)
     with torch.no_grad():
         assert_close(m(dev(x)), ref, PW_TOL["tf32x3"], "unfused fallback")
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 8, 12), (1, 5, 64, 64), (2, 2, 288, 288), (3, 4, 18, 20)])
+def test_cbam_pool_with_fused_maxpool(shape):
+    """smaat_cbam_pool_maxpool_fwd: global avg/max pools and MaxPool2d(2) from one read (layers.py:107-108, parts_ds.py:48)."""
+    x = rnd(*shape)
+    avg, mx, pooled = ops.cbam_pool_maxpool(dev(x))
+    B, C, H, W = shape
+    assert_close(avg, x.astype(np.float64).mean(axis=(2, 3)), 1e-5, "avg")
+    assert np.array_equal(mx.cpu().numpy(), x.max(axis=(2, 3)))
+    ref = x.reshape(B, C, H // 2, 2, W // 2, 2).max(axis=(3, 5))
+    assert np.array_equal(pooled.cpu().numpy(), ref)
+    assert ops.cbam_pool_maxpool(dev(rnd(1, 2, 9, 12))) is None and ops.cbam_pool_maxpool(dev(rnd(1, 2, 8, 10))) is None
