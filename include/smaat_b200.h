@@ -101,6 +101,10 @@ int smaat_dsconv_outconv_fwd(const float* x0, int C0, int64_t x0_bstride, const 
                              const float* scale, const float* shift, const float* oc_w, const float* oc_b, float* logits,
                              int B, int H, int W, int k, int Cout, int relu, int mode, void* stream);
 
+/* Debug hook: stage timers of the fused kernel's CTA 0 (16 clock64 counters accumulated over launches; layout in
+ * csrc/dsconv_fused.cu).  Copies them to the HOST array `out` and clears them; synchronises the device. */
+int smaat_debug_dsconv_timing(unsigned long long* out);
+
 /* 1 if this (x, w, K, Cout, P) can take the tcgen05 path (P % 4 == 0, K % 4 == 0, 16-byte aligned
  * pointers, Cout >= 8), else 0: the caller then uses SMAAT_PW_FP32_SIMT. */
 int smaat_pw1x1_tc_eligible(const float* x, const float* w, int K, int Cout, int P);

@@ -21,9 +21,17 @@
 //   warp 1      one lane issues tcgen05.mma kind::tf32 (1 or 3 per k-step) into TMEM, commits
 //   warps 2-5   epilogue: tcgen05.ld (lane = pixel) -> scale/shift/ReLU -> coalesced NCHW stores;
 //               two TMEM accumulator stages overlap it with the next tile's MMAs
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace smaat {
+
+// Stage timing of CTA 0 (clock64 cycles, accumulated over launches until read): see smaat_debug_dsconv_timing.
+//  [0] producer group 0: wait input box   [1] wait free A stage   [2] stencil + A-operand writes   [3] chunks
+//  [4] MMA lane: wait A   [5] wait B   [6] wait free accumulator   [7] issue   [8] chunks
+//  [9] epilogue warp 2: wait accumulator  [10] drain + store   [11] tiles      [12] kernel cycles
+__device__ unsigned long long g_ds_timing[16];
 
 struct DsParams {
   const float* dw_w;
@@ -38,6 +46,7 @@ struct DsParams {
   float* oc_y;
   int C0, C1, H, W, Cout, relu, K;
   int tiles_x, tiles_y, total_tiles, nchunks;
+  int timing;          // SMAAT_DSCONV_TIMING=1: CTA 0 records stage timers (debug)
 };
 
 template <int N_TILE, int KPL, int PW, bool X3>
@@ -132,6 +141,7 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const long long t_kernel0 = (p.timing && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
 
   if (warp == 0) {
     // ===== TMA: input halo boxes, running ahead through the IS-deep ring =====
@@ -190,13 +200,21 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
       uint32_t gc = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1u;
+        const bool rect = p.timing && (blockIdx.x == 0);
+        const long long te0 = rect ? clock64() : 0;
         mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1u) ^ 1u);
+        if (rect) atomicAdd(&g_ds_timing[6], (unsigned long long)(clock64() - te0));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * N_TILE;
         for (int i = 0; i < nch; ++i, ++gc) {
           const int sa = gc % AS, sb = gc % BS;
+          const bool rec = p.timing && (blockIdx.x == 0);
+          long long tk0 = 0, tk1 = 0, tk2 = 0;
+          if (rec) tk0 = clock64();
           mbar_wait(&a_full[sa], (gc / AS) & 1u);
+          if (rec) tk1 = clock64();
           mbar_wait(&b_full[sb], (gc / BS) & 1u);
+          if (rec) tk2 = clock64();
           tc_fence_after();
           const uint32_t a_addr = smem_u32(a_base + sa * L::AST_BYTES);
           const uint32_t b_addr = smem_u32(b_base + sb * L::BST_BYTES);
@@ -213,6 +231,13 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
           }
           umma_commit(&a_empty[sa]);  // each commit tracks completion of all MMAs issued so far
           umma_commit(&b_empty[sb]);
+          if (rec) {
+            const long long tk3 = clock64();
+            atomicAdd(&g_ds_timing[4], (unsigned long long)(tk1 - tk0));
+            atomicAdd(&g_ds_timing[5], (unsigned long long)(tk2 - tk1));
+            atomicAdd(&g_ds_timing[7], (unsigned long long)(tk3 - tk2));
+            atomicAdd(&g_ds_timing[8], 1ull);
+          }
         }
         umma_commit(&tmem_full[acc]);
       }
@@ -232,7 +257,11 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
       const int gy = ty * PH + pr, gx = tx * PW + pc;
       const bool pvalid = (gy < p.H) && (gx < p.W);
       const uint32_t acc = tcount & 1u;
+      const bool rec = p.timing && (blockIdx.x == 0) && (warp == 2) && (lane == 0);
+      long long tq0 = 0, tq1 = 0;
+      if (rec) tq0 = clock64();
       mbar_wait(&tmem_full[acc], (tcount >> 1) & 1u);
+      if (rec) tq1 = clock64();
       tc_fence_after();
       float* ypix = p.y + (int64_t)b * p.y_bstride + (int64_t)gy * p.W + gx;
       float oc_dot = 0.f;   // fused OutConv: this pixel's dot product over all Cout activations (lane = pixel)
@@ -295,6 +324,11 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
       if (p.oc_y && pvalid) p.oc_y[(int64_t)b * P + (int64_t)gy * p.W + gx] = oc_dot + (p.oc_b ? __ldg(p.oc_b) : 0.f);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
+      if (rec) {
+        atomicAdd(&g_ds_timing[9], (unsigned long long)(tq1 - tq0));
+        atomicAdd(&g_ds_timing[10], (unsigned long long)(clock64() - tq1));
+        atomicAdd(&g_ds_timing[11], 1ull);
+      }
     }
   } else {
     // ===== depthwise producer groups: warps 6-9 (group 0), 10-13 (group 1) =====
@@ -306,9 +340,14 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
       for (int i = 0; i < nch; ++i, ++gc) {
         if ((int)(gc & 1u) != g) continue;
         const int s = gc % IS;
+        const bool rec = p.timing && (blockIdx.x == 0) && (t == 0) && (g == 0);
+        long long tk0 = 0, tk1 = 0, tk2 = 0;
+        if (rec) tk0 = clock64();
         mbar_wait(&in_full[s], (gc / IS) & 1u);
+        if (rec) tk1 = clock64();
         const int sa = gc % AS;
         mbar_wait(&a_empty[sa], ((gc / AS) & 1u) ^ 1u);  // MMAs that read this A stage 3 chunks ago retired
+        if (rec) tk2 = clock64();
         unsigned char* my_op = a_base + sa * L::AST_BYTES;
         const float* in_stage = reinterpret_cast<const float*>(smem + s * L::IN_BYTES);
 #pragma unroll 1
@@ -387,10 +426,18 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         mbar_arrive(&a_full[sa]);
         mbar_arrive(&in_empty[s]);
+        if (rec) {
+          const long long tk3 = clock64();
+          atomicAdd(&g_ds_timing[0], (unsigned long long)(tk1 - tk0));
+          atomicAdd(&g_ds_timing[1], (unsigned long long)(tk2 - tk1));
+          atomicAdd(&g_ds_timing[2], (unsigned long long)(tk3 - tk2));
+          atomicAdd(&g_ds_timing[3], 1ull);
+        }
       }
     }
   }
   __syncthreads();
+  if (p.timing && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_ds_timing[12], (unsigned long long)(clock64() - t_kernel0));
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -509,6 +556,8 @@ static int dsconv_run(const float* x0, int C0, int64_t x0_bstride, const float* 
   DsParams p;
   p.dw_w = dw_w; p.dw_b = dw_b; p.scale = scale; p.shift = shift; p.y = y; p.y_bstride = y_bstride; p.stats = stats;
   p.oc_w = oc_w; p.oc_b = oc_b; p.oc_y = oc_y;
+  static const int timing_on = [] { const char* e = getenv("SMAAT_DSCONV_TIMING"); return (e && e[0] == '1') ? 1 : 0; }();
+  p.timing = timing_on;
   p.C0 = C0; p.C1 = C1; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu; p.K = K;
   p.tiles_x = p.tiles_y = p.total_tiles = p.nchunks = 0;
 
@@ -544,4 +593,16 @@ extern "C" int smaat_dsconv_outconv_fwd(const float* x0, int C0, int64_t x0_bstr
   SMAAT_REQUIRE(oc_w && logits, "dsconv+outconv: null pointer");
   return dsconv_run(x0, C0, x0_bstride, x1, C1, x1_bstride, dw_w, dw_b, pw_w, pw_w_lo, scale, shift, nullptr, 0, nullptr, oc_w, oc_b,
                     logits, B, H, W, k, Cout, relu, mode, stream);
+}
+
+/* Debug hook: copies the fused kernel's stage timers of CTA 0 (16 counters, clock64 cycles; layout in dsconv_fused.cu)
+ * to `out` and clears them.  Synchronises the device. */
+extern "C" int smaat_debug_dsconv_timing(unsigned long long* out) {
+  SMAAT_REQUIRE(out, "debug_dsconv_timing: null pointer");
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_ds_timing, sizeof(g_ds_timing));
+  if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "debug_dsconv_timing: %s", cudaGetErrorString(e));
+  unsigned long long z[16] = {0};
+  e = cudaMemcpyToSymbol(g_ds_timing, z, sizeof(z));
+  if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "debug_dsconv_timing: %s", cudaGetErrorString(e));
+  return SMAAT_OK;
 }
