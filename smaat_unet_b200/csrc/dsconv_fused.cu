@@ -74,7 +74,11 @@ struct DsCfg {
   static constexpr uint32_t B_TX = BST_BYTES;
   static constexpr int THREADS = 64 + 128 + 256 + 32;         // + warp 14: weight-ring loader
   static_assert(IS >= 2, "input ring");
-  static constexpr int TMEM_COLS = 2 * N_TILE;
+  // TF32X3: the weight stage holds [hi rows | lo rows] contiguously, so ONE N = 2*N_TILE MMA computes A_hi*[B_hi | B_lo]
+  // into 2*N_TILE accumulator columns and a second N = N_TILE MMA adds A_lo*B_hi to the first half: 2 instead of 3 MMAs
+  // per k-step (each MMA re-reads its 4 KB A slice from shared memory whatever N is); the epilogue adds the two halves.
+  static constexpr int ACC_COLS = X3 ? 2 * N_TILE : N_TILE;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;               // two accumulator stages
   static_assert(IN_BYTES % 128 == 0, "TMA destination alignment");
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
   static_assert(N_TILE <= AFF_N, "epilogue affine staging");
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* aff = reinterpret_cast<float*>(smem + L::OFF_BAR + L::BAR_BYTES);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too
   const int lane = threadIdx.x & 31;
   const int nch = p.nchunks;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const long long t_kernel0 = (p.timing && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
+  const long long t_kernel0 = ((p.timing & 1) && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
 
   if (warp == 0) {
     // ===== TMA: input halo boxes, running ahead through the IS-deep ring =====
@@ -186,7 +190,8 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         for (int i = 0; i < nch; ++i, ++gc) {
           const int sb = gc % BS;
-          mbar_wait(&b_empty[sb], ((gc / BS) & 1u) ^ 1u);
+          // rings of equal depth advance in lockstep: one commit (a_empty) releases both the A and the weight stage
+          mbar_wait((AS == BS) ? &a_empty[sb] : &b_empty[sb], ((gc / BS) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&b_full[sb], L::B_TX);
           tma_load_2d(b_base + sb * L::BST_BYTES, &map_w, &b_full[sb], i * TC_BK, 0);
           if (X3) tma_load_2d(b_base + sb * L::BST_BYTES + L::OFF_BLO, &map_wlo, &b_full[sb], i * TC_BK, 0);
@@ -194,52 +199,74 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(N_TILE);
-      uint32_t gc = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t acc = tcount & 1u;
-        const bool rect = p.timing && (blockIdx.x == 0);
-        const long long te0 = rect ? clock64() : 0;
-        mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1u) ^ 1u);
-        if (rect) atomicAdd(&g_ds_timing[6], (unsigned long long)(clock64() - te0));
+    // ===== MMA issuer: the whole warp walks the loop (warp-uniform control flow and descriptors, which the compiler keeps
+    // in uniform registers), one elected lane issues.  Descriptors are built once per chunk and advanced by constant adds:
+    // the issuing thread's own instruction stream was the limit (~30 SASS instructions, ~115 cycles per MMA before). =====
+    constexpr uint32_t idesc = make_idesc_tf32(N_TILE);
+    constexpr uint32_t idesc_wide = make_idesc_tf32(X3 ? 2 * N_TILE : N_TILE);
+    const bool rec = (p.timing & 1) && (blockIdx.x == 0) && (lane == 0);
+    uint32_t gc = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1u;
+      const long long te0 = rec ? clock64() : 0;
+      mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1u) ^ 1u);
+      if (rec) atomicAdd(&g_ds_timing[6], (unsigned long long)(clock64() - te0));
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * L::ACC_COLS;
+      for (int i = 0; i < nch; ++i, ++gc) {
+        const int sa = gc % AS, sb = gc % BS;
+        long long tk0 = 0, tk1 = 0, tk2 = 0;
+        if (rec) tk0 = clock64();
+        mbar_wait(&a_full[sa], (gc / AS) & 1u);
+        if (rec) tk1 = clock64();
+        mbar_wait(&b_full[sb], (gc / BS) & 1u);
+        if (rec) tk2 = clock64();
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N_TILE;
-        for (int i = 0; i < nch; ++i, ++gc) {
-          const int sa = gc % AS, sb = gc % BS;
-          const bool rec = p.timing && (blockIdx.x == 0);
-          long long tk0 = 0, tk1 = 0, tk2 = 0;
-          if (rec) tk0 = clock64();
-          mbar_wait(&a_full[sa], (gc / AS) & 1u);
-          if (rec) tk1 = clock64();
-          mbar_wait(&b_full[sb], (gc / BS) & 1u);
-          if (rec) tk2 = clock64();
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(a_base + sa * L::AST_BYTES);
           const uint32_t b_addr = smem_u32(b_base + sb * L::BST_BYTES);
+          // k-step kk: A advances 8 k-rows = 1 KB, the K-major weights 8 tf32 = 32 B (descriptor address field = bytes >> 4)
+          const uint64_t ad0 = make_a_desc(a_addr, TC_BK * 128);
+          const uint64_t al0 = make_a_desc(a_addr + L::OFF_ALO, TC_BK * 128);
+          const uint64_t bd0 = make_b_desc(b_addr);
           const int kc = min(TC_BK, p.K - i * TC_BK);
-          const int nmma = (kc + 7) >> 3;
-          for (int kk = 0; kk < nmma; ++kk) {
-            const uint64_t ad = make_a_desc(a_addr + kk * 1024, TC_BK * 128);
-            const uint64_t bd = make_b_desc(b_addr + kk * 32);
-            umma_tf32(d_tmem, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
-            if (X3) {
-              umma_tf32(d_tmem, make_a_desc(a_addr + L::OFF_ALO + kk * 1024, TC_BK * 128), bd, idesc, 1u);
-              umma_tf32(d_tmem, ad, make_b_desc(b_addr + L::OFF_BLO + kk * 32), idesc, 1u);
+          if (kc == TC_BK) {
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / 8; ++kk) {
+              const uint32_t first = (kk > 0) ? 1u : (i > 0 ? 1u : 0u);
+              if (X3) {
+                // D[:, 0:N) += A_hi*B_hi and D[:, N:2N) += A_hi*B_lo in one wide MMA over the contiguous hi|lo weight rows,
+                // then D[:, 0:N) += A_lo*B_hi
+                umma_tf32(d_tmem, ad0 + (uint64_t)(kk * 64), bd0 + (uint64_t)(kk * 2), idesc_wide, first);
+                umma_tf32(d_tmem, al0 + (uint64_t)(kk * 64), bd0 + (uint64_t)(kk * 2), idesc, 1u);
+              } else {
+                umma_tf32(d_tmem, ad0 + (uint64_t)(kk * 64), bd0 + (uint64_t)(kk * 2), idesc, first);
+              }
+            }
+          } else {
+            const int nmma = (kc + 7) >> 3;
+            for (int kk = 0; kk < nmma; ++kk) {
+              const uint32_t first = (i > 0 || kk > 0) ? 1u : 0u;
+              if (X3) {
+                umma_tf32(d_tmem, ad0 + (uint64_t)(kk * 64), bd0 + (uint64_t)(kk * 2), idesc_wide, first);
+                umma_tf32(d_tmem, al0 + (uint64_t)(kk * 64), bd0 + (uint64_t)(kk * 2), idesc, 1u);
+              } else {
+                umma_tf32(d_tmem, ad0 + (uint64_t)(kk * 64), bd0 + (uint64_t)(kk * 2), idesc, first);
+              }
             }
           }
           umma_commit(&a_empty[sa]);  // each commit tracks completion of all MMAs issued so far
-          umma_commit(&b_empty[sb]);
-          if (rec) {
-            const long long tk3 = clock64();
-            atomicAdd(&g_ds_timing[4], (unsigned long long)(tk1 - tk0));
-            atomicAdd(&g_ds_timing[5], (unsigned long long)(tk2 - tk1));
-            atomicAdd(&g_ds_timing[7], (unsigned long long)(tk3 - tk2));
-            atomicAdd(&g_ds_timing[8], 1ull);
-          }
+          if (AS != BS) umma_commit(&b_empty[sb]);
+          if (i == nch - 1) umma_commit(&tmem_full[acc]);
         }
-        umma_commit(&tmem_full[acc]);
+        __syncwarp();
+        if (rec) {
+          const long long tk3 = clock64();
+          atomicAdd(&g_ds_timing[4], (unsigned long long)(tk1 - tk0));
+          atomicAdd(&g_ds_timing[5], (unsigned long long)(tk2 - tk1));
+          atomicAdd(&g_ds_timing[7], (unsigned long long)(tk3 - tk2));
+          atomicAdd(&g_ds_timing[8], 1ull);
+        }
       }
     }
   } else if (warp < 6) {
@@ -257,7 +284,7 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
       const int gy = ty * PH + pr, gx = tx * PW + pc;
       const bool pvalid = (gy < p.H) && (gx < p.W);
       const uint32_t acc = tcount & 1u;
-      const bool rec = p.timing && (blockIdx.x == 0) && (warp == 2) && (lane == 0);
+      const bool rec = (p.timing & 1) && (blockIdx.x == 0) && (warp == 2) && (lane == 0);
       long long tq0 = 0, tq1 = 0;
       if (rec) tq0 = clock64();
       mbar_wait(&tmem_full[acc], (tcount >> 1) & 1u);
@@ -269,7 +296,15 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         if (c0 >= p.Cout) break;
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE + (uint32_t)c0, r);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * L::ACC_COLS + (uint32_t)c0;
+        tmem_ld32(taddr, r);
+        if (X3) {   // second half of the accumulator: the A_hi*B_lo term
+          uint32_t r2[32];
+          tmem_ld32(taddr + N_TILE, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
         float scv[32], shv[32];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -340,8 +375,23 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
       for (int i = 0; i < nch; ++i, ++gc) {
         if ((int)(gc & 1u) != g) continue;
         const int s = gc % IS;
-        const bool rec = p.timing && (blockIdx.x == 0) && (t == 0) && (g == 0);
+        const bool rec = (p.timing & 1) && (blockIdx.x == 0) && (t == 0) && (g == 0);
         long long tk0 = 0, tk1 = 0, tk2 = 0;
+        // depthwise weights of this thread's (first) task: issued before the ring waits so that their latency hides there
+        float wr[KPL][9], br[KPL];
+        auto task_channel = [&](int task) { return (PW == 32) ? (task >> 3) : (((task >> 4) << 1) | ((task >> 2) & 1)); };
+        auto load_weights = [&](int task) {
+          const int gch = i * CC + task_channel(task);
+          const bool chv = gch < Cin;
+#pragma unroll
+          for (int kk = 0; kk < KPL; ++kk) {
+            const int gk = gch * KPL + kk;
+#pragma unroll
+            for (int w9 = 0; w9 < 9; ++w9) wr[kk][w9] = chv ? __ldg(p.dw_w + (int64_t)gk * 9 + w9) : 0.f;
+            br[kk] = (chv && p.dw_b) ? __ldg(p.dw_b + gk) : 0.f;
+          }
+        };
+        load_weights(t);
         if (rec) tk0 = clock64();
         mbar_wait(&in_full[s], (gc / IS) & 1u);
         if (rec) tk1 = clock64();
@@ -365,16 +415,7 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
           }
           constexpr int NQ = PW / 4;
           const int c0 = qc << 2, r0 = rg << 2;
-          const int gch = i * CC + ci;  // global input channel of this task
-          float wr[KPL][9], br[KPL];
-          const bool chv = gch < Cin;
-#pragma unroll
-          for (int kk = 0; kk < KPL; ++kk) {
-            const int gk = gch * KPL + kk;
-#pragma unroll
-            for (int w9 = 0; w9 < 9; ++w9) wr[kk][w9] = chv ? __ldg(p.dw_w + (int64_t)gk * 9 + w9) : 0.f;
-            br[kk] = (chv && p.dw_b) ? __ldg(p.dw_b + gk) : 0.f;
-          }
+          if (task != t) load_weights(task);   // KPL = 1: a second task per chunk
           // smem column of patch column c (dx = -1..1) is c + 4 + dx: the 4 outputs read cols c0+3 .. c0+8
           const float* trow = in_stage + (ci * BH + r0) * BW + c0 + 3;
           float win[3][6];
@@ -437,7 +478,7 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
     }
   }
   __syncthreads();
-  if (p.timing && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_ds_timing[12], (unsigned long long)(clock64() - t_kernel0));
+  if ((p.timing & 1) && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_ds_timing[12], (unsigned long long)(clock64() - t_kernel0));
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -556,7 +597,7 @@ static int dsconv_run(const float* x0, int C0, int64_t x0_bstride, const float* 
   DsParams p;
   p.dw_w = dw_w; p.dw_b = dw_b; p.scale = scale; p.shift = shift; p.y = y; p.y_bstride = y_bstride; p.stats = stats;
   p.oc_w = oc_w; p.oc_b = oc_b; p.oc_y = oc_y;
-  static const int timing_on = [] { const char* e = getenv("SMAAT_DSCONV_TIMING"); return (e && e[0] == '1') ? 1 : 0; }();
+  static const int timing_on = [] { const char* e = getenv("SMAAT_DSCONV_TIMING"); return e ? atoi(e) : 0; }();
   p.timing = timing_on;
   p.C0 = C0; p.C1 = C1; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu; p.K = K;
   p.tiles_x = p.tiles_y = p.total_tiles = p.nchunks = 0;

@@ -57,7 +57,13 @@ struct PwTcCfg {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 2 * AFF_N * 4 + SACC_BYTES + 1024;  // + alignment slack
   static constexpr uint32_t TX_BYTES = A_BYTES + (X3 ? 2 : 1) * B_BYTES;
   static constexpr int THREADS = X3 ? 320 : 192;
-  static constexpr int TMEM_COLS = 2 * N_TILE;  // two accumulator stages
+  // TF32X3 with N_TILE <= 128: the stage holds the weight rows as [hi | lo] contiguously, so one N = 2*N_TILE MMA computes
+  // A_hi*[B_hi | B_lo] into 2*N_TILE accumulator columns and a second N = N_TILE MMA adds A_lo*B_hi to the first half --
+  // 2 instead of 3 MMAs per k-step (every MMA re-reads its 4 KB A slice from shared memory whatever N is); the epilogue
+  // adds the two halves.  N_TILE = 256 keeps three MMAs (an accumulator stage is limited to 256 of the 512 columns).
+  static constexpr bool WIDE = X3 && N_TILE <= 128;
+  static constexpr int ACC_COLS = WIDE ? 2 * N_TILE : N_TILE;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;  // two accumulator stages
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
@@ -144,13 +150,14 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(N_TILE);
+      constexpr uint32_t idesc_wide = make_idesc_tf32(L::WIDE ? 2 * N_TILE : N_TILE);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1u;
         const uint32_t acc_ph = (tcount >> 1) & 1u;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        const uint32_t d_tmem = tmem_base + acc * L::ACC_COLS;
         for (int i = 0; i < nk; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
@@ -166,12 +173,17 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
             const uint64_t ad = make_smem_desc(a_addr + kk * 1024, TC_BK * 128, 512, LAYOUT_SW128_BASE32B);
             // B (K-major, SW128): 8 tf32 = 32 B along the swizzled 128 B row; 8-row groups 1 KB apart (SBO)
             const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, LAYOUT_SW128);
-            umma_tf32(d_tmem, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
-            if (X3) {
-              const uint64_t ald = make_smem_desc(a_addr + L::OFF_ALO + kk * 1024, TC_BK * 128, 512, LAYOUT_SW128_BASE32B);
-              const uint64_t bld = make_smem_desc(a_addr + L::OFF_BLO + kk * 32, 16, 1024, LAYOUT_SW128);
-              umma_tf32(d_tmem, ald, bd, idesc, 1u);
-              umma_tf32(d_tmem, ad, bld, idesc, 1u);
+            if (L::WIDE) {
+              umma_tf32(d_tmem, ad, bd, idesc_wide, (i > 0 || kk > 0) ? 1u : 0u);   // A_hi * [B_hi | B_lo]
+              umma_tf32(d_tmem, make_smem_desc(a_addr + L::OFF_ALO + kk * 1024, TC_BK * 128, 512, LAYOUT_SW128_BASE32B), bd, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+              if (X3) {
+                const uint64_t ald = make_smem_desc(a_addr + L::OFF_ALO + kk * 1024, TC_BK * 128, 512, LAYOUT_SW128_BASE32B);
+                const uint64_t bld = make_smem_desc(a_addr + L::OFF_BLO + kk * 32, 16, 1024, LAYOUT_SW128);
+                umma_tf32(d_tmem, ald, bd, idesc, 1u);
+                umma_tf32(d_tmem, ad, bld, idesc, 1u);
+              }
             }
           }
           umma_commit(&empty_bar[s]);  // implicit tcgen05.fence::before_thread_sync
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         if (n0 + c0 >= p.Cout) break;
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N_TILE + (uint32_t)c0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * L::ACC_COLS + (uint32_t)c0;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -248,6 +260,13 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
           shv[4 * j4] = t.x; shv[4 * j4 + 1] = t.y; shv[4 * j4 + 2] = t.z; shv[4 * j4 + 3] = t.w;
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (L::WIDE) {   // second half of the accumulator: the A_hi*B_lo term
+          uint32_t r2[32];
+          tmem_ld32(taddr + N_TILE, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
         const int nch = min(32, p.Cout - (n0 + c0));  // warp-uniform
         float* yp = ypix + (int64_t)(n0 + c0) * p.P;
         if (nch == 32) {
@@ -269,7 +288,7 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
           // thread: 14 shuffles per 32 channels).  Pixels past P and channels past Cout are exact zeros (TMA zero fill),
           // so no masks; the epilogue affine is applied analytically when the sums are flushed.
           float s1, s2;
-          tmem_colsum32(taddr, lane, s1, s2);
+          tmem_colsum32<L::WIDE ? N_TILE : 0>(taddr, lane, s1, s2);
           const int col = c0 + tmem_colsum32_col(lane);
           sacc[col] += (double)s1;
           sacc[N_TILE + col] += (double)s2;

@@ -56,6 +56,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// One lane of the (converged) warp: the single-thread tcgen05 issue slot.  Unlike `if (lane == 0)` it keeps the
+// surrounding control flow warp-uniform for the compiler.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -98,6 +109,8 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&f)
 __device__ __forceinline__ int tmem_colsum32_col(int lane) {
   return 8 * (((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)) + 2 * (lane & 3) + ((lane >> 2) & 1);
 }
+// SECOND > 0: the value of a column is the sum of the accumulators at taddr and taddr + SECOND (split accumulation).
+template <int SECOND = 0>
 __device__ __forceinline__ void tmem_colsum32(uint32_t taddr, int lane, float& sum, float& sumsq) {
   float s1[8], s2[8];
 #pragma unroll
@@ -106,6 +119,13 @@ __device__ __forceinline__ void tmem_colsum32(uint32_t taddr, int lane, float& s
   for (int half = 0; half < 2; ++half) {
     uint32_t f[16];
     tmem_ld_16x256b_x4(taddr + ((uint32_t)(16 * half) << 16), f);
+    if (SECOND > 0) {
+      uint32_t f2[16];
+      tmem_ld_16x256b_x4(taddr + (uint32_t)SECOND + ((uint32_t)(16 * half) << 16), f2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = __float_as_uint(__uint_as_float(f[i]) + __uint_as_float(f2[i]));
+    }
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 4; ++i)
