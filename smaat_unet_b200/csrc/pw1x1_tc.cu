@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
   uint64_t* tmem_empty_bar = bars + 3 * STAGES + 2;  // [2] accumulator drained by the epilogue
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too
   const int lane = threadIdx.x & 31;
   const int nk = (p.K + TC_BK - 1) / TC_BK;
 
@@ -147,48 +147,56 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(N_TILE);
-      constexpr uint32_t idesc_wide = make_idesc_tf32(L::WIDE ? 2 * N_TILE : N_TILE);
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t acc = tcount & 1u;
-        const uint32_t acc_ph = (tcount >> 1) & 1u;
-        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator stage
+    // ===== MMA issuer: the whole warp walks the loop (warp-uniform control flow, descriptors in uniform registers), one
+    // elected lane issues; descriptors are built once per stage and advanced by constant adds per k-step =====
+    constexpr uint32_t idesc = make_idesc_tf32(N_TILE);
+    constexpr uint32_t idesc_wide = make_idesc_tf32(L::WIDE ? 2 * N_TILE : N_TILE);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1u;
+      const uint32_t acc_ph = (tcount >> 1) & 1u;
+      mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * L::ACC_COLS;
+      for (int i = 0; i < nk; ++i, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(X3 ? &xform_bar[s] : &full_bar[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * L::ACC_COLS;
-        for (int i = 0; i < nk; ++i, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(X3 ? &xform_bar[s] : &full_bar[s], ph);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + L::OFF_B;
+          // A (MN-major tf32, SW128 with 32 B atoms): one k-row = 128 B of pixels; 4-row swizzle groups 512 B apart (SBO),
+          // 8 k-rows per MMA = +1 KB per k-step (+64 in the descriptor's >>4 address field); 32-pixel blocks 4 KB apart (LBO)
+          const uint64_t ad0 = make_smem_desc(a_addr, TC_BK * 128, 512, LAYOUT_SW128_BASE32B);
+          const uint64_t al0 = make_smem_desc(a_addr + L::OFF_ALO, TC_BK * 128, 512, LAYOUT_SW128_BASE32B);
+          // B (K-major, SW128): 8 tf32 = 32 B along the swizzled 128 B row (+2 per k-step); 8-row groups 1 KB apart (SBO)
+          const uint64_t bd0 = make_smem_desc(a_addr + L::OFF_B, 16, 1024, LAYOUT_SW128);
+          const uint64_t bl0 = make_smem_desc(a_addr + L::OFF_BLO, 16, 1024, LAYOUT_SW128);
           const int kc = min(TC_BK, p.K - i * TC_BK);
-          const int nmma = (kc + 7) >> 3;
-          for (int kk = 0; kk < nmma; ++kk) {
-            // A (MN-major tf32, SW128 with 32 B atoms): one k-row = 128 B of pixels; 4-row swizzle groups
-            // 512 B apart (SBO), 8 k-rows per MMA = +1 KB per step; 32-pixel blocks 4 KB apart (LBO)
-            const uint64_t ad = make_smem_desc(a_addr + kk * 1024, TC_BK * 128, 512, LAYOUT_SW128_BASE32B);
-            // B (K-major, SW128): 8 tf32 = 32 B along the swizzled 128 B row; 8-row groups 1 KB apart (SBO)
-            const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, LAYOUT_SW128);
+          auto step = [&](int kk, uint32_t accum) {
+            const uint64_t ad = ad0 + (uint64_t)(kk * 64), bd = bd0 + (uint64_t)(kk * 2);
             if (L::WIDE) {
-              umma_tf32(d_tmem, ad, bd, idesc_wide, (i > 0 || kk > 0) ? 1u : 0u);   // A_hi * [B_hi | B_lo]
-              umma_tf32(d_tmem, make_smem_desc(a_addr + L::OFF_ALO + kk * 1024, TC_BK * 128, 512, LAYOUT_SW128_BASE32B), bd, idesc, 1u);
+              umma_tf32(d_tmem, ad, bd, idesc_wide, accum);                       // A_hi * [B_hi | B_lo]
+              umma_tf32(d_tmem, al0 + (uint64_t)(kk * 64), bd, idesc, 1u);         // A_lo * B_hi
             } else {
-              umma_tf32(d_tmem, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+              umma_tf32(d_tmem, ad, bd, idesc, accum);
               if (X3) {
-                const uint64_t ald = make_smem_desc(a_addr + L::OFF_ALO + kk * 1024, TC_BK * 128, 512, LAYOUT_SW128_BASE32B);
-                const uint64_t bld = make_smem_desc(a_addr + L::OFF_BLO + kk * 32, 16, 1024, LAYOUT_SW128);
-                umma_tf32(d_tmem, ald, bd, idesc, 1u);
-                umma_tf32(d_tmem, ad, bld, idesc, 1u);
+                umma_tf32(d_tmem, al0 + (uint64_t)(kk * 64), bd, idesc, 1u);
+                umma_tf32(d_tmem, ad, bl0 + (uint64_t)(kk * 2), idesc, 1u);
               }
             }
+          };
+          if (kc == TC_BK) {
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / 8; ++kk) step(kk, (kk > 0) ? 1u : (i > 0 ? 1u : 0u));
+          } else {
+            const int nmma = (kc + 7) >> 3;
+            for (int kk = 0; kk < nmma; ++kk) step(kk, (i > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);  // implicit tcgen05.fence::before_thread_sync
+          if (i == nk - 1) umma_commit(&tmem_full_bar[acc]);
         }
-        umma_commit(&tmem_full_bar[acc]);
+        __syncwarp();
       }
     }
   } else if (warp < 6) {

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(WgCfg<N_TILE, X3>::THREADS, 1)
   uint64_t* done_bar = bars + 3 * STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   // work item: (o tile, c tile, pixel split)
   const int tile = blockIdx.x % (p.tiles_o * p.tiles_c);
   const int split = blockIdx.x / (p.tiles_o * p.tiles_c);
@@ -100,27 +100,30 @@ __global__ void __launch_bounds__(WgCfg<N_TILE, X3>::THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32_kk(N_TILE);
-      for (int i = 0; i < nchunks; ++i) {
-        const int s = i % STAGES;
-        mbar_wait(X3 ? &xform_bar[s] : &full_bar[s], (i / STAGES) & 1u);
-        tc_fence_after();
+    // MMA issuer: whole warp in the loop (warp-uniform control flow, descriptors in uniform registers), one elected lane
+    // issues; both operands are K-major SW128 (8 tf32 = 32 B per k-step = +2 in the descriptor's >>4 address field)
+    constexpr uint32_t idesc = make_idesc_tf32_kk(N_TILE);
+    for (int i = 0; i < nchunks; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(X3 ? &xform_bar[s] : &full_bar[s], (i / STAGES) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + L::OFF_B;
+        const uint64_t ad0 = make_b_desc(a_addr), bd0 = make_b_desc(a_addr + L::OFF_B);
+        const uint64_t al0 = make_b_desc(a_addr + L::OFF_LO), bl0 = make_b_desc(a_addr + L::OFF_LO + L::OFF_B);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t ad = make_b_desc(a_addr + kk * 32);  // K-major SW128 descriptor (same form as the weights elsewhere)
-          const uint64_t bd = make_b_desc(b_addr + kk * 32);
-          umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          const uint64_t ad = ad0 + (uint64_t)(kk * 2), bd = bd0 + (uint64_t)(kk * 2);
+          umma_tf32(tmem_base, ad, bd, idesc, (kk > 0) ? 1u : (i > 0 ? 1u : 0u));
           if (X3) {
-            umma_tf32(tmem_base, make_b_desc(a_addr + L::OFF_LO + kk * 32), bd, idesc, 1u);
-            umma_tf32(tmem_base, ad, make_b_desc(b_addr + L::OFF_LO + kk * 32), idesc, 1u);
+            umma_tf32(tmem_base, al0 + (uint64_t)(kk * 2), bd, idesc, 1u);
+            umma_tf32(tmem_base, ad, bl0 + (uint64_t)(kk * 2), idesc, 1u);
           }
         }
         umma_commit(&empty_bar[s]);
+        if (i == nchunks - 1) umma_commit(done_bar);
       }
-      umma_commit(done_bar);
+      __syncwarp();
     }
   } else if (warp < 6) {
     // epilogue: TMEM lane = output channel o, column = input channel c
