@@ -61,8 +61,10 @@ struct DsCfg {
   static constexpr int BST_BYTES = (X3 ? 2 : 1) * B_BYTES;     // B ring stage: hi [+ lo]
   static constexpr int OFF_ALO = A_BYTES;
   static constexpr int OFF_BLO = B_BYTES;
-  static constexpr int AS = (KPL == 1 && X3 && N_TILE > 64) ? 2 : 3;  // A ring (2 producer groups alternate over it)
-  static constexpr int BS = X3 ? (N_TILE > 64 ? 2 : 3) : 4;     // weight ring, prefetched by the TMA warp
+  static constexpr int NG = 3;                                  // depthwise producer groups (128 threads each)
+  // A ring: 3 stages in TF32X3 (32 KB each; the input ring must stay deep enough to cover HBM latency), 4 in TF32
+  static constexpr int AS = X3 ? ((KPL == 1 && N_TILE > 64) ? 2 : 3) : 4;
+  static constexpr int BS = X3 ? 2 : 4;                         // weight ring, prefetched by its own warp
   static constexpr int IS_FIT = (218 * 1024 - AS * AST_BYTES - BS * BST_BYTES) / IN_BYTES;
   static constexpr int IS = IS_FIT > 8 ? 8 : IS_FIT;           // input ring: as deep as shared memory allows
   static constexpr int OFF_A = ((IS * IN_BYTES + 1023) / 1024) * 1024;
@@ -72,7 +74,8 @@ struct DsCfg {
   static constexpr int AFF_N = 128;
   static constexpr int TOTAL = OFF_BAR + BAR_BYTES + 3 * AFF_N * 4 + 1024;   // scale | shift | OutConv weights
   static constexpr uint32_t B_TX = BST_BYTES;
-  static constexpr int THREADS = 64 + 128 + 256 + 32;         // + warp 14: weight-ring loader
+  static constexpr int LOADER_WARP = 6 + 4 * NG;               // weight-ring loader
+  static constexpr int THREADS = 64 + 128 + 128 * NG + 32;     // TMA, MMA | 4 epilogue warps | producers | loader
   static_assert(IS >= 2, "input ring");
   // TF32X3: the weight stage holds [hi rows | lo rows] contiguously, so ONE N = 2*N_TILE MMA computes A_hi*[B_hi | B_lo]
   // into 2*N_TILE accumulator columns and a second N = N_TILE MMA adds A_lo*B_hi to the first half: 2 instead of 3 MMAs
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
         }
       }
     }
-  } else if (warp == 14) {
+  } else if (warp == L::LOADER_WARP) {
     // ===== weight-ring loader: K-major SW128 chunks (hi [+lo]), decoupled from the input ring =====
     if (lane == 0) {
       uint32_t gc = 0;
@@ -292,34 +295,54 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
       tc_fence_after();
       float* ypix = p.y + (int64_t)b * p.y_bstride + (int64_t)gy * p.W + gx;
       float oc_dot = 0.f;   // fused OutConv: this pixel's dot product over all Cout activations (lane = pixel)
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * L::ACC_COLS;
+      if (p.stats) {
+        // BatchNorm batch statistics from the RAW accumulators, re-read in fragment layout (tc_common.cuh); patch pixels
+        // outside the image are masked (their stencil still sees the image edge), channels past Cout are exact zeros (TMA
+        // zero fill of the weight rows); the affine is applied to the sums analytically
+        const uint32_t vmask = __ballot_sync(0xffffffffu, pvalid);
+        const double npix = (double)__popc(vmask);
 #pragma unroll 1
-      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+          if (c0 >= p.Cout) break;
+          float s1, s2;
+          tmem_colsum32<X3 ? N_TILE : 0>(tacc + (uint32_t)c0, lane, s1, s2, vmask);
+          const int c = c0 + tmem_colsum32_col(lane);
+          if (c < p.Cout) {
+            const double sc = (double)aff[c], sh = (double)aff[L::AFF_N + c];
+            atomicAdd(p.stats + c, sc * (double)s1 + npix * sh);
+            atomicAdd(p.stats + p.Cout + c, sc * sc * (double)s2 + 2.0 * sc * sh * (double)s1 + npix * sh * sh);
+          }
+        }
+      }
+      // 16 accumulator columns per step keep the epilogue within the 104-register budget of the 608-thread CTA
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 16) {
         if (c0 >= p.Cout) break;
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * L::ACC_COLS + (uint32_t)c0;
-        tmem_ld32(taddr, r);
+        uint32_t r[16];
+        tmem_ld16(tacc + (uint32_t)c0, r);
         if (X3) {   // second half of the accumulator: the A_hi*B_lo term
-          uint32_t r2[32];
-          tmem_ld32(taddr + N_TILE, r2);
+          uint32_t r2[16];
+          tmem_ld16(tacc + (uint32_t)(N_TILE + c0), r2);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
         }
-        float scv[32], shv[32];
+        float scv[16], shv[16];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
+        for (int j4 = 0; j4 < 4; ++j4) {
           const float4 a = *reinterpret_cast<const float4*>(aff + c0 + 4 * j4);
           const float4 t = *reinterpret_cast<const float4*>(aff + L::AFF_N + c0 + 4 * j4);
           scv[4 * j4] = a.x; scv[4 * j4 + 1] = a.y; scv[4 * j4 + 2] = a.z; scv[4 * j4 + 3] = a.w;
           shv[4 * j4] = t.x; shv[4 * j4 + 1] = t.y; shv[4 * j4 + 2] = t.z; shv[4 * j4 + 3] = t.w;
         }
         tmem_ld_wait();
-        const int nchn = min(32, p.Cout - c0);
+        const int nchn = min(16, p.Cout - c0);
         float* yp = ypix + (int64_t)c0 * P;
         if (p.oc_y) {
           // channels past Cout have zero accumulators, identity affine and zero OutConv weight: no mask needed
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
+          for (int j4 = 0; j4 < 4; ++j4) {
             const float4 w4 = *reinterpret_cast<const float4*>(aff + 2 * L::AFF_N + c0 + 4 * j4);
             const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
@@ -328,32 +351,18 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
               oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(r[j]), scv[j], shv[j]), act_lo), wv[e], oc_dot);
             }
           }
-        } else if (p.stats == nullptr && nchn == 32) {
+        } else if (nchn == 16) {
           if (pvalid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
               *yp = fmaxf(fmaf(__uint_as_float(r[j]), scv[j], shv[j]), act_lo);
               yp += P;
             }
           }
         } else {
 #pragma unroll
-          float m1[32], m2[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float pre = fmaf(__uint_as_float(r[j]), scv[j], shv[j]);
-            const float mv = (pvalid && j < nchn) ? pre : 0.f;
-            m1[j] = mv;
-            m2[j] = mv * mv;
-            if (pvalid && j < nchn) yp[(int64_t)j * P] = fmaxf(pre, act_lo);
-          }
-          if (p.stats) {  // BatchNorm batch statistics: 31-shuffle transpose-reduce, one fp64 atomic per channel
-            const float s1 = warp_transpose_sum32(m1, lane), s2 = warp_transpose_sum32(m2, lane);
-            if (lane < nchn) {
-              atomicAdd(p.stats + c0 + lane, (double)s1);
-              atomicAdd(p.stats + p.Cout + c0 + lane, (double)s2);
-            }
-          }
+          for (int j = 0; j < 16; ++j)
+            if (pvalid && j < nchn) yp[(int64_t)j * P] = fmaxf(fmaf(__uint_as_float(r[j]), scv[j], shv[j]), act_lo);
         }
       }
       if (p.oc_y && pvalid) p.oc_y[(int64_t)b * P + (int64_t)gy * p.W + gx] = oc_dot + (p.oc_b ? __ldg(p.oc_b) : 0.f);
@@ -366,14 +375,14 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
       }
     }
   } else {
-    // ===== depthwise producer groups: warps 6-9 (group 0), 10-13 (group 1) =====
+    // ===== depthwise producer groups: NG groups of 4 warps (warps 6 ..), group g takes every NG-th chunk =====
     const int g = (warp - 6) >> 2;
     const int t = threadIdx.x - 192 - 128 * g;  // 0..127
     const int Cin = p.C0 + p.C1;
     uint32_t gc = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       for (int i = 0; i < nch; ++i, ++gc) {
-        if ((int)(gc & 1u) != g) continue;
+        if ((int)(gc % (uint32_t)L::NG) != g) continue;
         const int s = gc % IS;
         const bool rec = (p.timing & 1) && (blockIdx.x == 0) && (t == 0) && (g == 0);
         long long tk0 = 0, tk1 = 0, tk2 = 0;

@@ -88,6 +88,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Fragment-shaped TMEM read: 16 lanes x 32 columns.  Thread T gets, for i = 0..3 and e = 0,1:
@@ -110,8 +118,9 @@ __device__ __forceinline__ int tmem_colsum32_col(int lane) {
   return 8 * (((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)) + 2 * (lane & 3) + ((lane >> 2) & 1);
 }
 // SECOND > 0: the value of a column is the sum of the accumulators at taddr and taddr + SECOND (split accumulation).
+// row_mask: bit l = TMEM lane l of this quarter takes part (rows whose accumulators are not exact zeros but must not count).
 template <int SECOND = 0>
-__device__ __forceinline__ void tmem_colsum32(uint32_t taddr, int lane, float& sum, float& sumsq) {
+__device__ __forceinline__ void tmem_colsum32(uint32_t taddr, int lane, float& sum, float& sumsq, uint32_t row_mask = 0xffffffffu) {
   float s1[8], s2[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v) s1[v] = s2[v] = 0.f;
@@ -127,11 +136,12 @@ __device__ __forceinline__ void tmem_colsum32(uint32_t taddr, int lane, float& s
       for (int i = 0; i < 16; ++i) f[i] = __float_as_uint(__uint_as_float(f[i]) + __uint_as_float(f2[i]));
     }
     tmem_ld_wait();
+    const bool va = (row_mask >> (16 * half + (lane >> 2))) & 1u, vb = (row_mask >> (16 * half + (lane >> 2) + 8)) & 1u;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const float a = __uint_as_float(f[4 * i + e]), b = __uint_as_float(f[4 * i + 2 + e]);
+        const float a = va ? __uint_as_float(f[4 * i + e]) : 0.f, b = vb ? __uint_as_float(f[4 * i + 2 + e]) : 0.f;
         s1[2 * i + e] += a + b;
         s2[2 * i + e] = fmaf(a, a, fmaf(b, b, s2[2 * i + e]));
       }
