@@ -295,8 +295,13 @@ def main():
         # DRAM traffic per launch from the ncu --set full capture of the same kernels (profiles/), GB; None if not captured
         roof = {"kernel": KNAMES.get(dom, dom) + f" ({d['launches_per_step']} launches/step)", "bound": "hbm",
                 "achieved": d["achieved_GBps"], "peak": hbm, "unit": "GB/s", "frac": d["frac_hbm"], "peak_source": src,
-                "traffic": None, "algorithmic_bytes_per_step": d["algorithmic_GB_per_step"] * 1e9, "ms_per_step": d["ms_per_step"],
-                "note": "fused DS conv is shared-memory-bandwidth bound; its algorithmic bytes are 2.8x fewer than dw+pw unfused (DESIGN.md 5)"
+                "traffic": 9.928e8 if dom == "smaat_dsconv_fwd" else None,
+                "traffic_note": "ncu --set full, dram read+write of ONE launch (up3.0: C256->128 @144^2): 992.8 MB vs 1019 MB "
+                                "algorithmic for that launch (profiles/r01c_ncu_summary.md); the 9 launches of a step differ in size"
+                if dom == "smaat_dsconv_fwd" else "",
+                "algorithmic_bytes_per_step": d["algorithmic_GB_per_step"] * 1e9, "ms_per_step": d["ms_per_step"],
+                "note": "fused DS conv: depthwise producers, tcgen05 issue and epilogue are balanced within ~10% (stage timers in "
+                        "profiles/r01_dsconv_stage_timers.txt); its algorithmic bytes are 2.8x fewer than dw+pw unfused (DESIGN.md 5)"
                 if dom == "smaat_dsconv_fwd" else ""}
         # the metric's named kernel -- "depthwise % HBM roofline": the standalone depthwise kernel over ALL 18 layers
         # (fusion switched off for this measurement pass only)
@@ -313,7 +318,7 @@ def main():
             g2 = a2["bytes"] / (a2["ms"] * 1e-3) / 1e9
             roof_dw = {"kernel": f"dw3x3_kernel ({a2['launches'] // 3} launches/step, all DS layers, unfused pass)", "bound": "hbm",
                        "achieved": g2, "peak": hbm, "unit": "GB/s", "frac": g2 / hbm, "peak_source": src,
-                       "traffic": 4.02e9, "traffic_note": "ncu dram read+write for the up4.0 launch: 4.02 GB vs 4.08 GB algorithmic (profiles/r01_ncu_summary_v1.md)",
+                       "traffic": 4.02e9, "traffic_note": "ncu dram read+write for the largest launch (up4.0): 4.02 GB vs 4.08 GB algorithmic (profiles/r01_ncu_summary_v1.md)",
                        "algorithmic_bytes_per_step": a2["bytes"] / 3, "ms_per_step": a2["ms"] / 3}
 
     # ---------------- CPU baseline (oracle port), rank 0, N=1 only ----------------

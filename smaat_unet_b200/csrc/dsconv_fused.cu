@@ -12,15 +12,18 @@
 //   warp 0      TMA: (PH+2) x (PW+8) x CC input halo box per chunk (OOB zero fill = padding=1; box
 //               starts at x0-4: the inner TMA coordinate must be 16-byte aligned) into an IS-deep ring;
 //               input may be the virtual concat [x0, x1] of UpDS (parts_ds.py:85)
-//   warps 6-13  two depthwise producer groups (128 threads each; each takes every other chunk, writing
-//               into a 3-stage A ring so a group never waits for its own chunk's MMAs): 3x3 stencil from the staged tile with a sliding register
-//               window, then write the result straight into the UMMA A-operand layout (MN-major tf32,
-//               128B span / 32B-atom swizzle) -- as hi and lo tf32 parts in TF32X3 mode (the split is
-//               free here: values are in registers); the weight chunks (K-major SW128, hi [+lo]) are
-//               prefetched by warp 14 into their own ring
-//   warp 1      one lane issues tcgen05.mma kind::tf32 (1 or 3 per k-step) into TMEM, commits
-//   warps 2-5   epilogue: tcgen05.ld (lane = pixel) -> scale/shift/ReLU -> coalesced NCHW stores;
-//               two TMEM accumulator stages overlap it with the next tile's MMAs
+//   warps 6-17  three depthwise producer groups (128 threads each; group g takes every third chunk): 3x3 stencil
+//               from the staged tile with a sliding register window (one LDS.128 per row, edge columns from the
+//               neighbouring quads by shuffle), then write the result straight into the UMMA A-operand layout
+//               (MN-major tf32, 128B span / 32B-atom swizzle) -- as hi and lo tf32 parts in TF32X3 mode (the split
+//               is free here: values are in registers) -- into a 3/4-stage A ring
+//   warp 18     prefetches the weight chunks (K-major SW128, [hi rows | lo rows]) into their own ring
+//   warp 1      MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma kind::tf32 into TMEM (TF32X3: a wide
+//               A_hi x [B_hi | B_lo] MMA + A_lo x B_hi per k-step) and commits
+//   warps 2-5   epilogue: tcgen05.ld (lane = pixel, 16 columns per step) -> scale/shift/ReLU -> coalesced NCHW stores
+//               (or the fused 1-class OutConv dot product; or BatchNorm batch statistics from fragment-shaped
+//               reads); two TMEM accumulator stages overlap it with the next tile's MMAs
+// Debug: SMAAT_DSCONV_TIMING=1 makes CTA 0 record per-stage cycle counters (smaat_debug_dsconv_timing).
 #include <stdlib.h>
 
 #include "tc_common.cuh"
