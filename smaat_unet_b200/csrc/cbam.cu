@@ -122,6 +122,45 @@ __global__ void __launch_bounds__(256) cbam_mlp_kernel(const float* __restrict__
 }
 
 // ---- per-pixel channel mean / max of x*sc --------------------------------------------------------------
+// Large planes: a thread owns 4 pixels and walks every channel with 8 independent 128-bit loads in flight -- no
+// cross-thread reduction, no barrier; s_c of the image is staged in shared memory.
+__global__ void __launch_bounds__(256) cbam_reduce_v4_kernel(const float* __restrict__ x, const float* __restrict__ sc,
+                                                             float* __restrict__ pooled, int C, int P4) {
+  extern __shared__ float scs[];
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) scs[c] = __ldg(sc + (int64_t)b * C + c);
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P4) return;
+  const float4* x4 = reinterpret_cast<const float4*>(x) + (int64_t)b * C * P4 + i;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  int c = 0;
+  for (; c + 8 <= C; c += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(x4 + (int64_t)(c + u) * P4);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float g = scs[c + u];
+      const float a0 = v[u].x * g, a1 = v[u].y * g, a2 = v[u].z * g, a3 = v[u].w * g;
+      s.x += a0; s.y += a1; s.z += a2; s.w += a3;
+      m.x = fmaxf(m.x, a0); m.y = fmaxf(m.y, a1); m.z = fmaxf(m.z, a2); m.w = fmaxf(m.w, a3);
+    }
+  }
+  for (; c < C; ++c) {
+    const float4 v = __ldg(x4 + (int64_t)c * P4);
+    const float g = scs[c];
+    const float a0 = v.x * g, a1 = v.y * g, a2 = v.z * g, a3 = v.w * g;
+    s.x += a0; s.y += a1; s.z += a2; s.w += a3;
+    m.x = fmaxf(m.x, a0); m.y = fmaxf(m.y, a1); m.z = fmaxf(m.z, a2); m.w = fmaxf(m.w, a3);
+  }
+  const float inv = 1.f / (float)C;
+  float4* pa = reinterpret_cast<float4*>(pooled) + (int64_t)b * 2 * P4 + i;
+  pa[0] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+  pa[P4] = m;
+}
+
 // blockDim = (32 pixel-quads, 8 channel groups); smem tree over the 8 groups.
 template <bool VEC>
 __global__ void __launch_bounds__(256) cbam_reduce_kernel(const float* __restrict__ x, const float* __restrict__ sc,
@@ -391,6 +430,12 @@ extern "C" int smaat_cbam_reduce_fwd(const float* x, const float* sc, float* poo
   SMAAT_REQUIRE(x && sc && pooled && B > 0 && C > 0 && P > 0, "cbam_reduce: bad arguments");
   SMAAT_REQUIRE(B <= 65535, "cbam_reduce: batch too large for grid.y");
   const bool vec = (P % 4 == 0) && aligned16(x) && aligned16(pooled);
+  if (vec && P >= 8192 && (size_t)C * sizeof(float) <= 48 * 1024) {
+    cbam_reduce_v4_kernel<<<dim3(ceil_div(P / 4, 256), B), 256, (size_t)C * sizeof(float), (cudaStream_t)stream>>>(x, sc, pooled, C,
+                                                                                                              P / 4);
+    SMAAT_LAUNCH_CHECK("smaat_cbam_reduce_fwd");
+    return SMAAT_OK;
+  }
   dim3 grid(ceil_div(P, 128), B), block(32, 8);
   if (vec) cbam_reduce_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(x, sc, pooled, C, P);
   else cbam_reduce_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(x, sc, pooled, C, P);
