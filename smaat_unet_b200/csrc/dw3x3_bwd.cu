@@ -239,9 +239,11 @@ __global__ void __launch_bounds__(256) dw3x3_bwd_input_tma(const __grid_constant
 
 template <int K, int RH, bool PRO>
 __global__ void __launch_bounds__(256) dw3x3_bwd_weight_tma(const __grid_constant__ CUtensorMap map0,
-                                                            const __grid_constant__ CUtensorMap map1, const DwbParams p) {
+                                                            const __grid_constant__ CUtensorMap map1,
+                                                            const __grid_constant__ CUtensorMap mapg, const DwbParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);   // [BH][BW] input halo tile
+  float* gt = tile + p.plane_floats;                  // [K][TH][TW] gradient tiles (one TMA box, K planes deep)
   __shared__ __align__(8) uint64_t bar;
   __shared__ float red[K * 10][8];
   const int tiles = p.tiles_x * p.tiles_y;
@@ -254,9 +256,10 @@ __global__ void __launch_bounds__(256) dw3x3_bwd_weight_tma(const __grid_constan
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_barrier_init();
-    mbar_arrive_expect_tx(&bar, (uint32_t)(BW * BH * sizeof(float)));
+    mbar_arrive_expect_tx(&bar, (uint32_t)((BW * BH + K * p.TW * p.TH) * sizeof(float)));
     if (c < p.C0) tma_load_4d(tile, &map0, &bar, x0 - 4, y0 - 1, c, b);
     else tma_load_4d(tile, &map1, &bar, x0 - 4, y0 - 1, c - p.C0, b);
+    tma_load_4d(gt, &mapg, &bar, x0, y0, c * K, b);   // all bytes in flight by bulk copy: no per-thread load latency
   }
   __syncthreads();
   mbar_wait(&bar, 0);
@@ -269,9 +272,8 @@ __global__ void __launch_bounds__(256) dw3x3_bwd_weight_tma(const __grid_constan
   for (int kk = 0; kk < K; ++kk)
 #pragma unroll
     for (int q = 0; q < 10; ++q) acc[kk][q] = 0.f;
-  const int P = p.H * p.W;
-  const float* g = p.g + ((int64_t)b * Cin + c) * K * P;
   const int nsx = p.TW >> 2, nsy = p.TH / RH;
+  const int gplane = p.TW * p.TH;
   for (int s = tid; s < nsx * nsy; s += blockDim.x) {
     const int sy = s / nsx, sx = s - sy * nsx;
     const int col = sx << 2, row0 = sy * RH;
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(256) dw3x3_bwd_weight_tma(const __grid_constan
     if (gx >= p.W || y0 + row0 >= p.H) continue;
     float win[3][6];
     const float* trow = tile + row0 * BW + col + 3;
+    const float* grow = gt + row0 * p.TW + col;
     const bool lpad = (gx == 0), rpad = (gx + 4 >= p.W);
     auto load_row = [&](float* wl, int r) {   // r: tile row relative to row0; image row y0 + row0 + r - 1
       load_row6(wl, trow + r * BW);
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(256) dw3x3_bwd_weight_tma(const __grid_constan
         const float* r2 = win[(i + 2) % 3];
 #pragma unroll
         for (int kk = 0; kk < K; ++kk) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + (int64_t)kk * P + (int64_t)gy * p.W + gx));
+          const float4 g4 = *reinterpret_cast<const float4*>(grow + kk * gplane + i * p.TW);   // rows past H: TMA zero fill
           const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -375,12 +378,12 @@ static int launch_dwb_input(const CUtensorMap& mg, const DwbParams& p, int64_t g
 }
 
 template <int K, int RH, bool PRO>
-static int launch_dwb_weight(const CUtensorMap& m0, const CUtensorMap& m1, const DwbParams& p, int64_t grid, int threads,
-                             cudaStream_t st) {
-  const size_t smem = (size_t)p.plane_floats * sizeof(float);
+static int launch_dwb_weight(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mg, const DwbParams& p, int64_t grid,
+                             int threads, cudaStream_t st) {
+  const size_t smem = ((size_t)p.plane_floats + (size_t)K * p.TW * p.TH) * sizeof(float);   // input halo tile + K gradient tiles
   auto kern = dw3x3_bwd_weight_tma<K, RH, PRO>;
   if (int r = dwb_set_smem(kern, smem, "dw3x3_bwd_weight")) return r;
-  kern<<<(unsigned)grid, threads, smem, st>>>(m0, m1, p);
+  kern<<<(unsigned)grid, threads, smem, st>>>(m0, m1, mg, p);
   SMAAT_LAUNCH_CHECK("smaat_dw3x3_bwd_weight");
   return SMAAT_OK;
 }
@@ -432,11 +435,20 @@ static int dwb_weight_try_tma(const float* dd, const float* x0, int C0, int64_t 
   } else {
     m1 = m0;
   }
+  CUtensorMap mg;   // gradient planes: one box = TW x TH x k planes of this input channel
+  memset(&mg, 0, sizeof(mg));
+  {
+    const int Cin = C0 + C1;
+    const uint32_t gbox[4] = {(uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)k, 1u};
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)Cin * k, (uint64_t)B};
+    const uint64_t str[4] = {0, (uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)Cin * k * H * W * 4};
+    if (int r = make_tmap_f32(&mg, dd, 4, dims, str, gbox, CU_TENSOR_MAP_SWIZZLE_NONE, "dw3x3_bwd_weight(dd)")) return r;
+  }
   const int64_t grid = (int64_t)B * (C0 + C1) * p.tiles_x * p.tiles_y;
   SMAAT_REQUIRE(grid < (1ll << 31), "dw3x3_bwd_weight: grid too large");
   const bool pro = in_scale != nullptr;
 #define SMAAT_DWB_W(KK, RR) \
-  (pro ? launch_dwb_weight<KK, RR, true>(m0, m1, p, grid, threads, st) : launch_dwb_weight<KK, RR, false>(m0, m1, p, grid, threads, st))
+  (pro ? launch_dwb_weight<KK, RR, true>(m0, m1, mg, p, grid, threads, st) : launch_dwb_weight<KK, RR, false>(m0, m1, mg, p, grid, threads, st))
   if (k == 1) return rh == 8 ? SMAAT_DWB_W(1, 8) : SMAAT_DWB_W(1, 4);
   return rh == 8 ? SMAAT_DWB_W(2, 8) : SMAAT_DWB_W(2, 4);
 #undef SMAAT_DWB_W
