@@ -297,7 +297,7 @@ def main():
                 "achieved": d["achieved_GBps"], "peak": hbm, "unit": "GB/s", "frac": d["frac_hbm"], "peak_source": src,
                 "traffic": 9.928e8 if dom == "smaat_dsconv_fwd" else None,
                 "traffic_note": "ncu --set full, dram read+write of ONE launch (up3.0: C256->128 @144^2): 992.8 MB vs 1019 MB "
-                                "algorithmic for that launch (profiles/r01c_ncu_summary.md); the 9 launches of a step differ in size"
+                                "algorithmic for that launch (profiles/r01d_ncu_summary.md); the 9 launches of a step differ in size"
                 if dom == "smaat_dsconv_fwd" else "",
                 "algorithmic_bytes_per_step": d["algorithmic_GB_per_step"] * 1e9, "ms_per_step": d["ms_per_step"],
                 "note": "fused DS conv: depthwise producers, tcgen05 issue and epilogue are balanced within ~10% (stage timers in "
