@@ -1,6 +1,7 @@
 /*
  * smaat_b200.h -- C ABI of libsmaat_b200.so: the B200 (sm_100a) kernels behind the
- * SmaAt-UNet forward hot path (depthwise-separable conv blocks + CBAM + their glue).
+ * SmaAt-UNet hot path (depthwise-separable conv blocks + CBAM + their glue): forward for
+ * inference, train-mode forward + backward, and the training step's loss/metric pass.
  *
  * The reference (HansBambel/SmaAt-UNet) has no FFI / plugin registry: its boundary is
  * the Python nn.Module interface.  Each entry point below
@@ -12,7 +13,8 @@
  *   - all tensors are fp32, NCHW, dense in (H, W); device pointers owned by the caller
  *     (PyTorch caching allocator).  The library allocates nothing persistent.
  *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*):
- *     no device synchronisation, no allocation -> CUDA-graph capturable.
+ *     no device synchronisation, no allocation -> CUDA-graph capturable
+ *     (the one exception is the debug hook smaat_debug_dsconv_timing).
  *   - return value: 0 on success, negative SMAAT_E_* otherwise; smaat_last_error()
  *     returns a thread-local description.  Nothing throws or exits across the ABI.
  *   - "bstride" arguments are batch strides in ELEMENTS (>= C*H*W) so a kernel can
