@@ -49,6 +49,15 @@ int make_tmap_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 
 int num_sms();
 
+// True the first time a call site sees the current device (`mask` is the call site's function-local static): per-device
+// one-time setup such as cudaFuncSetAttribute, which applies to the current device only.
+inline bool first_use_on_device(std::atomic<uint64_t>& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  return (mask.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // device-side PTX wrappers (mbarrier, TMA, fences)
 // ---------------------------------------------------------------------------------------

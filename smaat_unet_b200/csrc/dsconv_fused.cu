@@ -503,11 +503,10 @@ static int launch_ds(const CUtensorMap& m0, const CUtensorMap& m1, const CUtenso
                      int B, cudaStream_t st) {
   using L = DsCfg<N_TILE, KPL, PW, X3>;
   auto kern = dsconv_fused_kernel<N_TILE, KPL, PW, X3>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_mask{0};   // cudaFuncSetAttribute is per device
+  if (first_use_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "dsconv: smem attribute (%d B): %s", L::TOTAL, cudaGetErrorString(e));
-    attr_done = true;
   }
   p.tiles_x = ceil_div(p.W, PW);
   p.tiles_y = ceil_div(p.H, L::PH);

@@ -348,11 +348,10 @@ template <int N_TILE, int STAGES, bool X3>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mwl, PwTcParams p, int B, cudaStream_t st) {
   using L = PwTcCfg<N_TILE, STAGES, X3>;
   auto kern = pw1x1_tc_kernel<N_TILE, STAGES, X3>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_mask{0};   // cudaFuncSetAttribute is per device
+  if (first_use_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "pw1x1(tc): smem attribute (%d B): %s", L::TOTAL, cudaGetErrorString(e));
-    attr_done = true;
   }
   p.tiles_m = ceil_div(p.P, TC_BM);
   p.tiles_n = ceil_div(p.Cout, N_TILE);

@@ -186,11 +186,10 @@ template <int N_TILE, bool X3>
 static int launch_wg(const CUtensorMap& mz, const CUtensorMap& md, WgParams p, cudaStream_t st) {
   using L = WgCfg<N_TILE, X3>;
   auto kern = pw1x1_wgrad_kernel<N_TILE, X3>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_mask{0};   // cudaFuncSetAttribute is per device
+  if (first_use_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "pw1x1_wgrad: smem attribute: %s", cudaGetErrorString(e));
-    attr_done = true;
   }
   p.tiles_o = ceil_div(p.Cout, TC_BM);
   p.tiles_c = ceil_div(p.K, N_TILE);

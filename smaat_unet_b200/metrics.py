@@ -114,7 +114,7 @@ class PrecipitationMetrics:
 
     def __getattr__(self, name):
         names = type(self)._NAMES
-        if name in names:
+        if name in names and "_totals" in self.__dict__:
             v = self.__dict__["_totals"][names.index(name)]
             return v if name.startswith("total_loss") else v.to(torch.int64)
         raise AttributeError(name)
