@@ -6,6 +6,7 @@ reference's own classes (``patch_reference``), and the functional kernel wrapper
 All arithmetic runs in ``libsmaat_b200.so`` (C ABI: ``include/smaat_b200.h``).
 """
 from . import _lib, ops  # noqa: F401
+from .data import PinnedBatchLoader, precipitation_maps_oversampled_shard, precipitation_maps_shard  # noqa: F401
 from .metrics import PrecipitationMetrics, loss_func, step_loss  # noqa: F401
 from .model import SmaAt_UNet  # noqa: F401
 from .modules import (CBAM, ChannelAttention, DepthwiseSeparableConv, DoubleConvDS, DownDS, OutConv,  # noqa: F401

@@ -129,6 +129,13 @@ class TrainSession:
         self.y.copy_(sy, non_blocking=True)
         self._slot_free[i].record(self.stream)
 
+    def last_h2d_event(self):
+        """Event marking the end of the most recent host->device batch copy (None before the first host batch).  Hand it to
+        ``PinnedBatchLoader.guard`` so the loader does not overwrite a pinned buffer that is still being copied."""
+        if not hasattr(self, "_slots") or self._n == 0:
+            return None
+        return self._h2d_done[(self._n - 1) % 2]
+
     def load_batch(self, x, y):
         """Copy a batch into the static input buffers (async).  Host tensors (pinned for true overlap) are staged on a
         separate copy stream so the transfer of step i+1 hides behind the compute of step i."""
