@@ -254,3 +254,33 @@ def test_train_session_matches_eager_steps(use_graph):
     assert int(sess.metrics.total_samples) == 3 * B
     assert int(m1.state_dict()["inc.double_conv.1.num_batches_tracked"]) == 3
 
+
+
+def test_train_session_fed_by_pinned_loader_matches_direct_batches():
+    """PinnedBatchLoader (pinned ring, background fill, guard events) -> TrainSession gives the same losses as feeding the
+    same samples as device tensors."""
+    from smaat_unet_b200 import data as D
+    from smaat_unet_b200.train import TrainSession
+    rng = np.random.default_rng(7)
+    arr = rng.random((12, 13, 32, 32), dtype=np.float32)            # 12 samples, 12 inputs + target
+    ds = D.precipitation_maps_oversampled_shard(arr, 12, 1)
+    torch.manual_seed(5)
+    m1 = S.SmaAt_UNet(12, 1, kernels_per_layer=2).cuda().train()
+    m2 = S.SmaAt_UNet(12, 1, kernels_per_layer=2).cuda().train()
+    m2.load_state_dict(m1.state_dict())
+    s1 = TrainSession(m1, 4, (12, 32, 32), use_graph=True)
+    s2 = TrainSession(m2, 4, (12, 32, 32), use_graph=True)
+    loader = D.PinnedBatchLoader(ds, batch_size=4, ring=2)
+    l1, l2 = [], []
+    for bi, (x, y) in enumerate(loader):
+        assert x.is_pinned() and y.is_pinned()
+        l1.append(s1.step(x, y).clone())
+        loader.guard(s1.last_h2d_event())
+        xb = torch.from_numpy(arr[bi * 4:(bi + 1) * 4, :12]).cuda()
+        yb = torch.from_numpy(arr[bi * 4:(bi + 1) * 4, -1]).cuda()
+        l2.append(s2.step(xb, yb).clone())
+    torch.cuda.synchronize()
+    assert len(l1) == 3
+    assert abs(float(l1[0]) - float(l2[0])) <= 1e-5 * abs(float(l2[0]))      # same batch, same weights
+    for a, b in zip(l1[1:], l2[1:]):                                           # later steps: chaotic drift bound (see above)
+        assert abs(float(a) - float(b)) <= 2e-2 * abs(float(b))
