@@ -46,6 +46,37 @@ class DoubleConvDSFn(torch.autograd.Function):
         return (None, dx if need[1] else None, dx1 if need[2] else None, *pg)
 
 
+class DSConvFn(torch.autograd.Function):
+    """A standalone DepthwiseSeparableConv (layers.py:47-50): depthwise then pointwise, both biases, no BN/activation."""
+
+    @staticmethod
+    def run(mod, x):
+        for p in (mod.depthwise.bias, mod.pointwise.bias):
+            if p is None:
+                raise NotImplementedError("DepthwiseSeparableConv without conv biases is not supported in the autograd path")
+        return DSConvFn.apply(mod, x, mod.depthwise.weight, mod.depthwise.bias, mod.pointwise.weight, mod.pointwise.bias)
+
+    @staticmethod
+    def forward(ctx, mod, x, *params):
+        x = ops._dense(x, "x")
+        d, z = Fn.ds_conv_fwd(mod, x)              # unfused: the depthwise result is needed by the weight gradient
+        ctx.mod = mod
+        ctx.save_for_backward(x, d)
+        return z
+
+    @staticmethod
+    def backward(ctx, g):
+        x, d = ctx.saved_tensors
+        mod, need = ctx.mod, ctx.needs_input_grad
+        g = ops._dense(g, "grad_output")
+        zeros = lambda p: torch.zeros(p.shape, device=p.device, dtype=torch.float32)
+        dWd, dbd, dWp, dbp = zeros(mod.depthwise.weight), zeros(mod.depthwise.bias), zeros(mod.pointwise.weight), zeros(mod.pointwise.bias)
+        dd = Fn.pw_bwd(g, d, mod.pointwise.weight, dWp, dbp)
+        dx, _ = Fn.dw_bwd(dd, mod.depthwise.weight, x, None, None, None, mod.kernels_per_layer, dWd, dbd, need_input=need[1])
+        grads = [dWd, dbd, dWp, dbp]
+        return (None, dx if need[1] else None, *[gi if need[2 + i] else None for i, gi in enumerate(grads)])
+
+
 class CBAMFn(torch.autograd.Function):
     @staticmethod
     def params(mod):

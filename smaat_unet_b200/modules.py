@@ -91,7 +91,10 @@ class DepthwiseSeparableConv(nn.Module):
         return ops.pw1x1(d, self.pointwise.weight.detach(), scale, shift, relu, mode=mode, w_split=split, stats=stats)
 
     def forward(self, x):
-        _no_autograd(self, x)
+        if _needs_grad(self, x):
+            from .autograd import DSConvFn
+            self._check()
+            return DSConvFn.run(self, x)
         return self.run(x)
 
 

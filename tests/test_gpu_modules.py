@@ -79,8 +79,8 @@ def test_standalone_attention_modules():
 def test_unsupported_requests_are_refused_loudly_not_silently_wrong():
     with pytest.raises(NotImplementedError):          # ConvTranspose2d upsampling branch (parts_ds.py:72-73)
         S.UpDS(8, 4, bilinear=False).cuda().eval()(torch.zeros(1, 4, 4, 4, device="cuda"), torch.zeros(1, 4, 8, 8, device="cuda"))
-    with pytest.raises(NotImplementedError):          # standalone DS conv has no autograd node (the blocks do)
-        S.DepthwiseSeparableConv(4, 8, 3, padding=1).cuda()(torch.zeros(1, 4, 8, 8, device="cuda"))
+    with pytest.raises(NotImplementedError):          # standalone attention halves have no autograd node (CBAM does)
+        S.ChannelAttention(16).cuda()(torch.zeros(1, 16, 8, 8, device="cuda"))
     with pytest.raises(NotImplementedError):          # only the reference's 3x3 / padding=1 depthwise exists
         with torch.no_grad():
             S.DepthwiseSeparableConv(4, 8, 5, padding=2).cuda()(torch.zeros(1, 4, 8, 8, device="cuda"))

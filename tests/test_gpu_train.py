@@ -54,7 +54,9 @@ def _cpu_reference(kind, c, sd_np, xs_np, train, R, dtype=torch.float64):
         sd[k] = t.to(dtype).requires_grad_(True) if t.dtype != torch.int64 and not k.endswith(("running_mean", "running_var")) \
             else (t.to(dtype) if t.dtype != torch.int64 else t)
     xs = [torch.from_numpy(x).to(dtype).requires_grad_(True) for x in xs_np]
-    if kind == "doubleconv":
+    if kind == "dsconv":
+        y = TP.ds_conv(xs[0], sd, "m")
+    elif kind == "doubleconv":
         y = TP.double_conv_ds(xs[0], sd, "m", train)
     elif kind == "down":
         y = TP.down_ds(xs[0], sd, "m", train)
@@ -73,7 +75,7 @@ def _cpu_reference(kind, c, sd_np, xs_np, train, R, dtype=torch.float64):
     return y.detach().double().numpy(), grads, [x.grad.double().numpy() for x in xs]
 
 
-GRAD_CASES = ["doubleconv_eval", "doubleconv_mid_eval", "doubleconv_train", "down_eval", "up_eval_even", "up_eval_pad",
+GRAD_CASES = ["dsconv_k1", "dsconv_k2", "dsconv_k3", "doubleconv_eval", "doubleconv_mid_eval", "doubleconv_train", "down_eval", "up_eval_even", "up_eval_pad",
               "cbam_k7_eval", "cbam_k3_eval", "cbam_k7_train", "outconv", "unet_12_1_k2_32", "unet_12_1_k2_train", "unet_3_5_k1_48"]
 
 
@@ -82,7 +84,7 @@ GRAD_CASES = ["doubleconv_eval", "doubleconv_mid_eval", "doubleconv_train", "dow
 def test_gradients_match_cpu_autograd(name, train):
     c = CASES[name]
     kind = c["kind"]
-    if kind == "outconv" and train:
+    if kind in ("outconv", "dsconv") and train:
         pytest.skip("no mode dependence")
     sd_np, xs_np = case_tensors(name, np.float64)
     mod, prefix = build(c)
