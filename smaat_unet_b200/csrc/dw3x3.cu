@@ -226,6 +226,10 @@ static void pick_tile(int H, int W, int* TW, int* TH, int* RH) {
 
 void dw_pick_tile(int H, int W, int* TW, int* TH, int* RH) { pick_tile(H, W, TW, TH, RH); }  // shared with dw3x3_bwd.cu
 
+// dw3x3_small.cu: returns 1 when not applicable
+int dw3x3_small_try(const float* x0, int C0, int64_t bs0, const float* x1, int C1, int64_t bs1, const float* w, const float* bias,
+                    const float* in_scale, const float* in_shift, float* y, int B, int H, int W, int k, cudaStream_t st);
+
 template <int K, int RH, bool USE_TMA, bool PRO, bool VEC>
 static int launch_dw(const CUtensorMap& m0, const CUtensorMap& m1, const DwParams& p, int threads, size_t smem,
                      int64_t grid, cudaStream_t st) {
@@ -294,6 +298,10 @@ extern "C" int smaat_dw3x3_fwd(const float* x0, int C0, int64_t x0_bstride, cons
   SMAAT_REQUIRE(loader >= 0 && loader <= 2, "dw3x3: loader must be 0 (auto), 1 (ldg) or 2 (tma)");
   SMAAT_REQUIRE(!(loader == 2 && !tma_ok), "dw3x3: TMA loader forced but ineligible (W %% 4 = %d, alignment)", W % 4);
   const bool use_tma = (loader == 1) ? false : tma_ok;
+  if (loader == 0 && !tma_ok) {   // small planes TMA cannot describe (e.g. 18 x 18): one warp per plane (dw3x3_small.cu)
+    const int r = dw3x3_small_try(x0, C0, x0_bstride, x1, C1, x1_bstride, w, bias, in_scale, in_shift, y, B, H, W, k, st);
+    if (r != 1) return r;
+  }
 
   CUtensorMap m0, m1;
   memset(&m0, 0, sizeof(m0));

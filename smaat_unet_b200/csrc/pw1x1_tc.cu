@@ -373,6 +373,7 @@ int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const flo
   SMAAT_REQUIRE(pw1x1_tc_eligible(x, w, w_lo, K, Cout, P), "pw1x1(tc): needs P %% 4 == 0, K %% 4 == 0 and 16-byte aligned x/w");
   SMAAT_REQUIRE(!x3 || w_lo, "pw1x1(tc): TF32X3 needs w_lo (see smaat_split_tf32)");
   SMAAT_REQUIRE(Cout <= 512 || (!scale && !shift), "pw1x1(tc): Cout=%d > 512 with an epilogue affine (smem staging holds 512 channels)", Cout);
+  // the tile shape depends on the layer only, never on the batch: results stay bit-identical across batch sizes
   const int n_tile = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
 
   CUtensorMap mx, mw, mwl;

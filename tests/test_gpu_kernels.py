@@ -19,11 +19,12 @@ def rnd(*shape, lo=-1.0, hi=1.0):
 # ------------------------------------------------------------------------------ depthwise
 DW_CASES = [
     # B, C0, C1, H, W, k, loaders
-    (2, 5, 0, 9, 11, 1, (1,)),          # W % 4 != 0 -> LDG only, ragged tiles
+    (2, 5, 0, 9, 11, 1, (0, 1)),        # W % 4 != 0 -> LDG loader / one-warp-per-plane kernel (auto)
     (2, 6, 0, 12, 8, 2, (1, 2)),
     (1, 4, 0, 7, 5, 3, (1,)),           # generic k
     (2, 3, 5, 16, 20, 2, (1, 2)),       # virtual concat
-    (1, 8, 0, 18, 18, 2, (1,)),         # the 18x18 layers (72-byte rows: no TMA)
+    (1, 8, 0, 18, 18, 2, (0, 1)),       # the 18x18 layers (72-byte rows: no TMA): auto = one warp per plane
+    (3, 5, 4, 18, 18, 2, (0, 1)),       # ... over a virtual concat, several images
     (2, 4, 0, 36, 36, 2, (1, 2)),
     (1, 3, 0, 72, 72, 2, (1, 2)),
     (1, 2, 2, 144, 144, 2, (1, 2)),
@@ -55,9 +56,9 @@ def test_dw3x3_matches_oracle(case):
     assert_close(y, O.depthwise3x3(x.astype(np.float64), w, None, k), 2e-6, "dw3x3 no-bias")
 
 
-@pytest.mark.parametrize("loader", [1, 2])
+@pytest.mark.parametrize("loader", [0, 1, 2])
 def test_dw3x3_prologue_bn_relu_then_zero_pad(loader):
-    B, C, H, W, k = 2, 6, 12, 16, 2
+    B, C, H, W, k = (2, 6, 12, 16, 2) if loader else (2, 6, 9, 10, 2)     # loader 0 on a W % 4 != 0 plane: one-warp-per-plane kernel
     x, w, b = rnd(B, C, H, W), rnd(k * C, 1, 3, 3), rnd(k * C)
     s, t = rnd(C, lo=0.5, hi=1.5), rnd(C)
     act = np.maximum(x.astype(np.float64) * s[None, :, None, None] + t[None, :, None, None], 0)
