@@ -176,11 +176,14 @@ int smaat_outconv_fwd(const float* x, const float* w, const float* bias, float* 
                       int B, int Cin, int ncls, int P, void* stream);
 
 /* ======================================= backward (training step) =======================================
- * Gradients of the same path (BASELINE configs[2]); notation: z = pre-BatchNorm activation,
+ * Gradients of the same path (BASELINE configs[2]): what torch autograd runs for these modules when the reference calls
+ * loss.backward() (train_SmaAtUNet.py:55; Lightning automatic optimisation over UNetBase.training_step,
+ * models/regression_lightning.py:67-78).  Each group names the forward lines it differentiates.  Notation: z = pre-BatchNorm activation,
  * a = act(scale*z+shift), dA = dL/da masked by the activation (act: 0 none, 1 ReLU recomputed from z).
  * Accumulating outputs (dW, db, dgamma, dbeta, d_sc, stats-like sums) are += : the caller zero-initialises.
  *
- * BatchNorm(+ReLU) backward = reduce -> coeffs -> apply:
+ * BatchNorm(+ReLU) backward -- nn.BatchNorm2d + nn.ReLU, parts_ds.py:25-26,34-35; BatchNorm2d(1), layers.py:120,127 --
+ * = reduce -> coeffs -> apply:
  *   reduce: sums[c] += sum dA, sums[C+c] += sum dA*z                       (fp64)
  *   coeffs: dgamma += invstd*(S2 - mean*S1), dbeta += S1; per-channel a,b,cc with dz = a*dA + b*z + cc
  *           (train: batch-statistics terms; eval (train=0): dz = gamma*invstd*dA); dz_sum (nullable) += sum_{b,p} dz
@@ -193,7 +196,7 @@ int smaat_bn_bwd_coeffs(const double* sums, double count, const float* gamma, co
 int smaat_bn_act_bwd_apply(const float* dy, const float* z, const float* scale, const float* shift,
                            const float* a, const float* b, const float* cc, float* dz, int B, int C, int P, int act, void* stream);
 
-/* depthwise 3x3 backward: input gradient (split over the virtual concat x0|x1) and weight/bias gradient;
+/* depthwise 3x3 backward (DepthwiseSeparableConv.depthwise, models/layers.py:38-44,48): input gradient (split over the virtual concat x0|x1) and weight/bias gradient;
  * in_scale/in_shift: the forward's on-load BN+ReLU prologue (input of the conv was relu(in_scale*x+in_shift)). */
 int smaat_dw3x3_bwd_input(const float* dd, const float* w, float* dx0, int C0, int64_t dx0_bstride,
                           float* dx1, int C1, int64_t dx1_bstride, int B, int H, int W, int k, void* stream);
@@ -201,7 +204,8 @@ int smaat_dw3x3_bwd_weight(const float* dd, const float* x0, int C0, int64_t x0_
                            const float* in_scale, const float* in_shift, float* dw, float* db,
                            int B, int H, int W, int k, void* stream);
 
-/* pointwise 1x1: dW[o][c] += sum_{b,p} dz[b,o,p]*d[b,c,p], db[o] += sum dz.  (The input gradient is
+/* pointwise 1x1 backward (DepthwiseSeparableConv.pointwise, models/layers.py:45,49): dW[o][c] += sum_{b,p} dz[b,o,p]*d[b,c,p],
+ * db[o] += sum dz.  (The input gradient is
  * smaat_pw1x1_fwd(dz, W^T): use smaat_transpose for W^T.) */
 int smaat_pw1x1_bwd_weight(const float* dz, const float* d, float* dW, float* db, int B, int K, int Cout, int P, void* stream);
 /* tensor-core (tcgen05, split over pixels + fp32 atomics) variant; mode SMAAT_PW_TF32 / SMAAT_PW_TF32X3;
@@ -210,12 +214,14 @@ int smaat_pw1x1_bwd_weight_tc(const float* dz, const float* d, float* dW, float*
                               int mode, void* stream);
 int smaat_transpose(const float* src, float* dst, int rows, int cols, void* stream);
 
+/* glue backward: nn.MaxPool2d(2) (parts_ds.py:48), nn.Upsample(x2, bilinear, align_corners) + F.pad (parts_ds.py:64,78-81),
+ * OutConv (unet_parts.py:67-73) */
 int smaat_maxpool2_bwd(const float* x, const float* dy, float* dx, int64_t N, int H, int W, void* stream);
 int smaat_upsample2x_pad_bwd(const float* dy, int64_t dy_bstride, float* dx, int B, int C, int H, int W, int Ho, int Wo, void* stream);
 int smaat_outconv_bwd(const float* dy, const float* x, const float* w, float* dx, float* dW, float* db,
                       int B, int Cin, int ncls, int P, void* stream);
 
-/* CBAM backward (see cbam_bwd.cu for the chain): gate_in -> [BN(1) backward] -> gate_bwd -> dsc -> mlp_bwd -> dx.
+/* CBAM backward (models/layers.py:90-141 differentiated; see cbam_bwd.cu for the chain): gate_in -> [BN(1) backward] -> gate_bwd -> dsc -> mlp_bwd -> dx.
  * amax: (B, P) int32 channel argmax of x*sc written by gate_in; pkey: (B*C) uint64, zeroed by the caller, receives the
  * packed plane argmax of x in dsc and is consumed by dx; dsc (B, C) is accumulated into (caller zeroes it). */
 int smaat_cbam_bwd_gate_in(const float* g, const float* x, const float* sc, const float* sa, float* dpre, int* amax,
