@@ -34,11 +34,35 @@ B_PER_GPU, C_IN, SIZE = 32, 12, 288
 
 
 def peaks():
+    """(HBM GB/s, dense tf32 TFLOP/s, source).  tf32 tensor peak = half the measured cuBLAS bf16 burst figure (a kernel
+    timed launch by launch); nominal ratio bf16:tf32 = 2:1 (B200_PROFILING.md)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]) / 2.0, "measured (MEASURED_PEAKS.json; tf32 = bf16 burst / 2)"
+    return 6650.0, 1590.0 / 2.0, "fallback (B200_PROFILING.md; tf32 = bf16 / 2)"
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes (read + write) of one launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summarize.py from the .ncu-rep); None when there is no capture of the
+    current kernel -- never a constant in this file."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p)).get(kernel_key)
+        return (d["dram_bytes_per_launch"], d["note"]) if d else (None, "")
+    except Exception:
+        return None, ""
 
 
 def randomise_bn(model, gen):
@@ -134,6 +158,38 @@ def cpu_port_time(n_frames, reps, threads):
     return ts
 
 
+def eager_gpu_baseline(model, xs, dev):
+    """Reported-only: the reference's algorithm as eager PyTorch ops (ATen / cuDNN through oracle/torch_port.py) on the same
+    GPU, same weights and B=32 input -- what a user of the unmodified reference gets on this box
+    (train_precip_lightning.py:53-55), with cudnn.allow_tf32 False and True.  CUDA events, 3 warm-up + 5 timed forwards."""
+    from oracle import torch_port as TP
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    out = {"unit": "frames/s", "batch": int(xs[0].shape[0]), "how": "oracle/torch_port.py on cuda (ATen/cuDNN eager, no graph), 3 warm-up + 5 timed"}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for flag in (False, True):
+            torch.backends.cudnn.allow_tf32 = flag
+            torch.backends.cuda.matmul.allow_tf32 = flag
+            with torch.no_grad():
+                for i in range(3):
+                    TP.smaat_unet_forward(xs[i % 2], sd)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(5):
+                    TP.smaat_unet_forward(xs[i % 2], sd)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            out["allow_tf32_true" if flag else "allow_tf32_false"] = {"value": xs[0].shape[0] / (ms * 1e-3), "ms_per_step": ms}
+    except Exception as e:          # a reported-only leg must never take the bench line down
+        out["error"] = repr(e)[:200]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -205,24 +261,44 @@ def main():
     def reduce_max(v):
         return PAR.reduce_max(v, dev)
 
+    def timed_replays(session):
+        """W warm-up + K timed graph replays on alternating resident inputs; CUDA events, barrier + sync both sides, max over ranks."""
+        for i in range(args.warmup):
+            session.forward(xs[i % 2])
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(args.steps):
+            session.forward(xs[i % 2])
+        a1.record()
+        barrier()
+        return reduce_max(a0.elapsed_time(a1))
+
     # ---------------- device-resident throughput ("value") ----------------
-    for i in range(args.warmup):
-        sess.forward(xs[i % 2])
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    n0 = S._lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        sess.forward(xs[i % 2])
-    e1.record()
-    barrier()
-    ms = reduce_max(e0.elapsed_time(e1))
-    eager_launches = S._lib.launch_count() - n0
+    ms = timed_replays(sess)
     clocks = sampler.result()
     fps = world * B_PER_GPU * args.steps / (ms * 1e-3)
-    launches = (sess.launches_per_forward * args.steps) if sess.graph is not None else eager_launches
+    launches = sess.launches_per_forward * args.steps        # C-ABI launches of one forward (counted at capture) x timed steps
+
+    # ---------------- parity of the timed path, outside the timed region (rank 0) ----------------
+    # two frames of the graph-replayed B=32 output vs the CPU restatement of the reference on the same input
+    parity = None
+    expect = [float(sess.forward(host[i].to(dev))[0, 0, 0, 0]) for i in range(2)]     # what e2e's checksum must add up to
+    if rank == 0 and not args.no_cpu_baseline:
+        import numpy as np
+        from oracle import torch_port as TP
+        sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        fr = [3, 29]
+        y_dev = sess.forward(xs[0])[fr].double().cpu().numpy()
+        torch.set_num_threads(usable_cpus())
+        with torch.no_grad():
+            y_ref = TP.smaat_unet_forward(xs[0][fr].cpu(), sd_cpu).double().numpy()
+        err = float(np.abs(y_dev - y_ref).max() / np.abs(y_ref).max())
+        tol = {"tf32x3": 1e-4, "fp32": 1e-4, "tf32": 2e-2}[args.mode]
+        parity = {"frames_checked": fr, "max_rel_err_vs_cpu_port": err, "tolerance": tol}
+        assert err <= tol, f"bench: the timed path disagrees with the oracle: {err:.3e} > {tol:.1e}"
 
     # ---------------- end to end through the public API, host buffers ----------------
     for i in range(args.warmup):
@@ -240,6 +316,19 @@ def main():
     e2e_s = reduce_max(time.perf_counter() - t0)
     barrier()
     e2e_fps = world * B_PER_GPU * args.steps / e2e_s
+    chk_expect = sum(expect[i % 2] for i in range(args.steps))
+    assert abs(chk - chk_expect) <= 1e-6 * max(1.0, abs(chk_expect)), \
+        f"bench: e2e results are not the results of the submitted batches (checksum {chk!r} != {chk_expect!r})"
+
+    # ---------------- the same forward through the plain reference-order calls only ----------------
+    # (what a patch_reference() user of the unchanged reference classes executes: no OutConv-in-epilogue fusion)
+    sess_api = InferenceSession(model, B_PER_GPU, (C_IN, SIZE, SIZE), device=dev, use_graph=not args.no_graph, serving_fusions=False)
+    api_ms = timed_replays(sess_api)
+    via_api = {"value": world * B_PER_GPU * args.steps / (api_ms * 1e-3), "unit": "frames/s", "ms_per_step": api_ms / args.steps,
+               "gap_to_value": 1.0 - (ms / api_ms), "launches_per_step": sess_api.launches_per_forward,
+               "note": "blocks called plainly in the reference's order (models/SmaAt_UNet.py:41-57); the CBAM->DownDS max-pool fusion is "
+                       "reached through the plain calls, the OutConv epilogue fusion is not expressible there (standalone 1x1 kernel)"}
+    del sess_api
 
     # ---------------- reported-only: same measurement in the single-pass TF32 mode ----------------
     # (what the reference itself computes on a GPU: cuDNN allow_tf32=True; ~1e-3 relative error instead of 1e-6)
@@ -247,30 +336,28 @@ def main():
     if args.mode == "tf32x3" and not args.no_alt:
         S.set_pointwise_mode("tf32")
         sess2 = InferenceSession(model, B_PER_GPU, (C_IN, SIZE, SIZE), device=dev, use_graph=not args.no_graph)
-        for i in range(args.warmup):
-            sess2.forward(xs[i % 2])
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for i in range(args.steps):
-            sess2.forward(xs[i % 2])
-        a1.record()
-        barrier()
-        ams = reduce_max(a0.elapsed_time(a1))
+        ams = timed_replays(sess2)
         alt = {"pointwise": "tf32", "value": world * B_PER_GPU * args.steps / (ams * 1e-3), "unit": "frames/s", "ms_per_step": ams / args.steps}
         del sess2
         S.set_pointwise_mode(args.mode)
+        S.ops.bump_weights_generation()
+
+    # ---------------- reported-only: eager PyTorch (ATen/cuDNN) on the SAME GPU -- the practical bar ----------------
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gpu_eager = eager_gpu_baseline(model, xs, dev)
 
     # ---------------- roofline: per-kernel timing, CUDA events on the launching stream ----------------
     roof, roof_dw, kernels = None, None, {}
     if rank == 0:
-        hbm, src = peaks()
+        hbm, tf32_peak, src = peaks()
+        fwd = model.forward_serving
         with torch.no_grad():
-            model(xs[0])
+            fwd(xs[0])
             torch.cuda.synchronize()
             with S.ops.profile() as prof:
                 for i in range(3):
-                    model(xs[i % 2])
+                    fwd(xs[i % 2])
             agg = prof.summary()
             # the last DS conv carries the fused OutConv epilogue (its own ABI entry): same kernel, count it with the others
             oc = agg.pop("smaat_dsconv_outconv_fwd", None)
@@ -283,26 +370,35 @@ def main():
                 for name, a in prof.summary(by_shape=True).items():
                     if "[" in name:
                         print(f"# {name:40s} {a['ms'] / 3:8.3f} ms  {a['bytes'] / a['ms'] / 1e6:7.0f} GB/s  {a['flops'] / a['ms'] / 1e9:7.1f} TF", file=sys.stderr)
+        # tensor-core kernels issue 3 tf32 MMAs per product in tf32x3 mode (1 in tf32): issued flops = passes x algorithmic GEMM flops
+        passes = {"tf32x3": 3.0, "tf32": 1.0, "fp32": 0.0}[args.mode]
+        TENSOR = ("smaat_dsconv_fwd", "smaat_pw1x1_fwd")
         for name, a in agg.items():
-            gbs = a["bytes"] / (a["ms"] * 1e-3) / 1e9 if a["ms"] > 0 else 0.0
+            sec = a["ms"] * 1e-3
+            gbs = a["bytes"] / sec / 1e9 if sec > 0 else 0.0
+            tfl = a["flops"] / sec / 1e12 if sec > 0 else 0.0
             kernels[name] = {"launches_per_step": a["launches"] // 3, "ms_per_step": a["ms"] / 3, "algorithmic_GB_per_step": a["bytes"] / 3e9,
-                             "achieved_GBps": gbs, "frac_hbm": gbs / hbm, "tflops": a["flops"] / (a["ms"] * 1e-3) / 1e12 if a["ms"] > 0 else 0.0}
+                             "achieved_GBps": gbs, "frac_hbm": gbs / hbm, "tflops": tfl}
+            if name in TENSOR:
+                kernels[name]["tf32_tflops_issued"] = passes * tfl
+                kernels[name]["frac_tensor"] = passes * tfl / tf32_peak
         # dominant kernel of the measured path (by time): its own algorithmic bytes / its own time
-        KNAMES = {"smaat_dsconv_fwd": "dsconv_fused_kernel (depthwise 3x3 -> tcgen05 pointwise -> BN/ReLU, one kernel)",
+        KNAMES = {"smaat_dsconv_fwd": "fused DS conv (depthwise 3x3 -> tcgen05 pointwise -> BN/ReLU, one kernel)",
                   "smaat_pw1x1_fwd": "pw1x1_tc_kernel", "smaat_dw3x3_fwd": "dw3x3_kernel"}
         dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
         d = kernels[dom]
-        # DRAM traffic per launch from the ncu --set full capture of the same kernels (profiles/), GB; None if not captured
-        roof = {"kernel": KNAMES.get(dom, dom) + f" ({d['launches_per_step']} launches/step)", "bound": "hbm",
-                "achieved": d["achieved_GBps"], "peak": hbm, "unit": "GB/s", "frac": d["frac_hbm"], "peak_source": src,
-                "traffic": 9.928e8 if dom == "smaat_dsconv_fwd" else None,
-                "traffic_note": "ncu --set full, dram read+write of ONE launch (up3.0: C256->128 @144^2): 992.8 MB vs 1019 MB "
-                                "algorithmic for that launch (profiles/r01d_ncu_summary.md); the 9 launches of a step differ in size"
-                if dom == "smaat_dsconv_fwd" else "",
+        traffic, tnote = ncu_traffic(dom)
+        f_h, f_t = d["frac_hbm"], d.get("frac_tensor", 0.0)
+        # the bound is whichever floor is closer: both fractions are reported, `frac` is the one of the binding resource
+        bound = "tensor" if f_t > f_h else "hbm"
+        roof = {"kernel": KNAMES.get(dom, dom) + f" ({d['launches_per_step']} launches/step)", "bound": bound,
+                "achieved": d["tf32_tflops_issued"] if bound == "tensor" else d["achieved_GBps"],
+                "peak": tf32_peak if bound == "tensor" else hbm, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                "frac": f_t if bound == "tensor" else f_h, "frac_hbm": f_h, "frac_tensor": f_t, "peak_hbm_GBps": hbm,
+                "peak_tf32_TFLOPs": tf32_peak, "peak_source": src, "traffic": traffic, "traffic_note": tnote,
                 "algorithmic_bytes_per_step": d["algorithmic_GB_per_step"] * 1e9, "ms_per_step": d["ms_per_step"],
-                "note": "fused DS conv: depthwise producers, tcgen05 issue and epilogue are balanced within ~10% (stage timers in "
-                        "profiles/r01_dsconv_stage_timers.txt); its algorithmic bytes are 2.8x fewer than dw+pw unfused (DESIGN.md 5)"
-                if dom == "smaat_dsconv_fwd" else ""}
+                "note": "frac_tensor counts ISSUED tf32 flops (3 MMA passes per product in tf32x3) against half the measured bf16 "
+                        "cuBLAS peak; frac_hbm counts algorithmic bytes (input + output of the fused conv) against the measured copy bandwidth"}
         # the metric's named kernel -- "depthwise % HBM roofline": the standalone depthwise kernel over ALL 18 layers
         # (fusion switched off for this measurement pass only)
         S.set_fused_dsconv(False)
@@ -316,19 +412,21 @@ def main():
         S.set_fused_dsconv(True)
         if a2:
             g2 = a2["bytes"] / (a2["ms"] * 1e-3) / 1e9
+            t2, n2 = ncu_traffic("smaat_dw3x3_fwd")
             roof_dw = {"kernel": f"dw3x3_kernel ({a2['launches'] // 3} launches/step, all DS layers, unfused pass)", "bound": "hbm",
                        "achieved": g2, "peak": hbm, "unit": "GB/s", "frac": g2 / hbm, "peak_source": src,
-                       "traffic": 4.02e9, "traffic_note": "ncu dram read+write for the largest launch (up4.0): 4.02 GB vs 4.08 GB algorithmic (profiles/r01_ncu_summary_v1.md)",
+                       "traffic": t2, "traffic_note": n2,
                        "algorithmic_bytes_per_step": a2["bytes"] / 3, "ms_per_step": a2["ms"] / 3}
 
-    # ---------------- CPU baseline (oracle port), rank 0, N=1 only ----------------
+    # ---------------- CPU baseline (oracle port), rank 0, N=1 only: the full B=32 batch, once ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = usable_cpus()
-        n = 8
+        n = B_PER_GPU
         ts = cpu_port_time(n, 1, threads)
-        cpu = {"value": n / ts[0], "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": f"1 timed forward of {n} frames 12x{SIZE}x{SIZE} after a 1-frame warm-up; oracle/torch_port.py (torch CPU fp32, {threads} threads)"}
+        cpu = {"value": n / ts[0], "unit": "frames/s", "cores": threads, "kind": "port", "cpu_model": cpu_model_name(),
+               "sample": f"1 timed forward of the full batch ({n} frames 12x{SIZE}x{SIZE}) after a 1-frame warm-up; oracle/torch_port.py "
+                         f"(torch CPU fp32, {threads} threads)"}
 
     if rank == 0:
         out = {
@@ -341,7 +439,9 @@ def main():
                        "l2": "inputs alternate between 2 buffers; a step streams ~40 GB of activations (>> 126 MB L2)"},
             "roofline": roof, "depthwise_roofline": roof_dw, "kernels": kernels, "cpu_baseline": cpu,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": sess.h2d_bytes_per_step,
-                    "d2h_bytes_per_step": sess.d2h_bytes_per_step, "ms_per_step": 1e3 * e2e_s / args.steps, "checksum": chk},
+                    "d2h_bytes_per_step": sess.d2h_bytes_per_step, "ms_per_step": 1e3 * e2e_s / args.steps, "checksum": chk,
+                    "checksum_expected": chk_expect},
+            "parity": parity, "via_reference_api": via_api, "gpu_eager_baseline": gpu_eager,
             "alt_mode": alt, "clocks": clocks, "gpu_launches": int(launches),
         }
         print(json.dumps(out), flush=True)

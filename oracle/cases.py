@@ -55,12 +55,13 @@ def cbam_schema(prefix, c, r=16, ks=7):
     return s
 
 
-def smaat_unet_schema(n_channels, n_classes, k=2, r=16):
-    # models/SmaAt_UNet.py:23-39 (bilinear=True -> factor 2)
+def smaat_unet_schema(n_channels, n_classes, k=2, r=16, n_cbams=5):
+    # models/SmaAt_UNet.py:23-39 (bilinear=True -> factor 2); n_cbams = 4 / 0: the Lightning variants
+    # UNetDSAttention4CBAMs / UNetDS (models/unet_precip_regression_lightning.py:167-208, 86-117)
     s = {}
     s.update(double_conv_ds_schema("inc", n_channels, 64, None, k))
     chans = [64, 128, 256, 512, 512]
-    for i in range(5):
+    for i in range(n_cbams):
         s.update(cbam_schema(f"cbam{i + 1}", chans[i], r))
     for i in range(1, 5):
         s.update(double_conv_ds_schema(f"down{i}.maxpool_conv.1", chans[i - 1], chans[i], None, k))
@@ -136,6 +137,11 @@ CASES = {
     "unet_12_1_k2_odd": dict(kind="unet", n_channels=12, n_classes=1, k=2, x=(1, 12, 36, 52), seed=82, train=False),
     "unet_3_5_k1_48": dict(kind="unet", n_channels=3, n_classes=5, k=1, x=(2, 3, 48, 48), seed=83, train=False),
     "unet_12_1_k2_train": dict(kind="unet", n_channels=12, n_classes=1, k=2, x=(2, 12, 32, 32), seed=84, train=True),
+    # the Lightning wrappers' own forward bodies (models/unet_precip_regression_lightning.py): UNetDSAttention (:148-164),
+    # UNetDSAttention4CBAMs (:193-208, x5 goes to the decoder un-attended), UNetDS (:104-117, no CBAM)
+    "lit_dsatt_k2_32": dict(kind="lit", cls="UNetDSAttention", n_cbams=5, n_channels=12, n_classes=1, k=2, x=(2, 12, 32, 32), seed=91, train=False),
+    "lit_dsatt4_k2_48": dict(kind="lit", cls="UNetDSAttention4CBAMs", n_cbams=4, n_channels=12, n_classes=1, k=2, x=(1, 12, 48, 48), seed=92, train=False),
+    "lit_ds_k1_32": dict(kind="lit", cls="UNetDS", n_cbams=0, n_channels=12, n_classes=1, k=1, x=(2, 12, 32, 32), seed=93, train=False),
 }
 
 
@@ -159,6 +165,8 @@ def case_schema(c):
         return s
     if kind == "unet":
         return smaat_unet_schema(c["n_channels"], c["n_classes"], c["k"])
+    if kind == "lit":
+        return smaat_unet_schema(c["n_channels"], c["n_classes"], c["k"], n_cbams=c["n_cbams"])
     raise KeyError(kind)
 
 
@@ -166,7 +174,7 @@ def case_tensors(name, dtype=np.float64):
     """(state_dict, inputs) for a case, as numpy arrays of ``dtype``."""
     c = CASES[name]
     sd = cast_sd(fill_schema(case_schema(c), c["seed"]), dtype)
-    lo = 0.0 if c["kind"] in ("unet",) else -1.0
+    lo = 0.0 if c["kind"] in ("unet", "lit") else -1.0
     xs = [rand_input(c["x"], c["seed"] + 1000, lo, 1.0).astype(dtype)]
     if "skip" in c:
         xs.append(rand_input(c["skip"], c["seed"] + 2000, -1.0, 1.0).astype(dtype))
@@ -198,4 +206,6 @@ def run_oracle(name, dtype=np.float64):
         return y, u
     if kind == "unet":
         return O.smaat_unet_forward(xs[0], sd, c["k"], train, return_updates=True)
+    if kind == "lit":
+        return O.smaat_unet_forward(xs[0], sd, c["k"], train, return_updates=True, n_cbams=c["n_cbams"])
     raise KeyError(kind)

@@ -67,6 +67,13 @@ def build_reference_module(c):
         return Block()
     if kind == "unet":
         return SmaAt_UNet(c["n_channels"], c["n_classes"], kernels_per_layer=c["k"])
+    if kind == "lit":
+        # the Lightning wrapper classes themselves, constructor and forward unmodified, under stand-ins for the
+        # imports that are not installed here (oracle/ref_stubs.py)
+        from oracle import ref_stubs
+        ref_stubs.install()
+        import models.unet_precip_regression_lightning as L          # noqa: E402
+        return getattr(L, c["cls"])(hparams=ref_stubs.hparams(c["n_channels"], c["n_classes"], c["k"]))
     raise KeyError(kind)
 
 
@@ -75,6 +82,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     index = {}
+    only = set(sys.argv[1:])          # optional: regenerate only the named cases (index.json is always rewritten in full)
     for name, c in CASES.items():
         mod = build_reference_module(c).double()
         ref_sd = mod.state_dict()
@@ -88,6 +96,10 @@ def main():
         mod.train(train)
         with torch.no_grad():
             y = mod(*[torch.from_numpy(x) for x in xs])
+        index[name] = {"output_shape": list(y.shape), "train": train,
+                       "abs_max": float(y.abs().max()), "n_params": int(sum(int(np.prod(s)) for s in schema.values()))}
+        if only and name not in only:
+            continue
         store = np.float32 if c.get("store") == "f4" else np.float64
         arrays = {"output": y.numpy().astype(store)}
         if train:
@@ -96,8 +108,6 @@ def main():
                 if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
                     arrays["buf:" + k] = v.numpy()
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
-        index[name] = {"output_shape": list(y.shape), "train": train,
-                       "abs_max": float(y.abs().max()), "n_params": int(sum(int(np.prod(s)) for s in schema.values()))}
         print(f"{name:28s} out={tuple(y.shape)} absmax={index[name]['abs_max']:.4f}")
     meta = {"reference": "HansBambel/SmaAt-UNet @ /root/reference", "torch": torch.__version__,
             "reference_pins_torch": "2.6.0", "dtype": "float64 (config1_block stored as float32)", "cases": index}

@@ -243,11 +243,12 @@ def out_conv(x, sd, prefix):
     return pointwise1x1(x, sd[prefix + ".conv.weight"], sd[prefix + ".conv.bias"])
 
 
-def smaat_unet_forward(x, sd, kernels_per_layer=2, training=False, return_updates=False):
+def smaat_unet_forward(x, sd, kernels_per_layer=2, training=False, return_updates=False, n_cbams=5):
     """SmaAt_UNet.forward (models/SmaAt_UNet.py:41-57), bilinear=True.
 
     Un-attended maps feed the next encoder stage, attended maps are the decoder
-    skips, x5Att is the decoder input.
+    skips, x5Att is the decoder input.  n_cbams = 4: UNetDSAttention4CBAMs (x5 un-attended,
+    unet_precip_regression_lightning.py:193-208); n_cbams = 0: UNetDS (:104-117).
     """
     k = kernels_per_layer
     upd = {}
@@ -260,7 +261,7 @@ def smaat_unet_forward(x, sd, kernels_per_layer=2, training=False, return_update
     enc = [acc(double_conv_ds(x, sd, "inc", k, training))]
     for i in range(1, 5):
         enc.append(acc(down_ds(enc[-1], sd, f"down{i}", k, training)))
-    att = [acc(cbam(e, sd, f"cbam{i + 1}", training)) for i, e in enumerate(enc)]
+    att = [acc(cbam(e, sd, f"cbam{i + 1}", training)) if i < n_cbams else e for i, e in enumerate(enc)]
     y = att[4]
     for i in range(1, 5):
         y = acc(up_ds(y, att[4 - i], sd, f"up{i}", k, training))

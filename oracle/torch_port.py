@@ -67,12 +67,12 @@ def cbam(x, sd, p, training=False):
     return x * torch.sigmoid(a)
 
 
-def smaat_unet_forward(x, sd, training=False):
-    # SmaAt_UNet.py:41-57
+def smaat_unet_forward(x, sd, training=False, n_cbams=5):
+    # SmaAt_UNet.py:41-57; n_cbams = 4 / 0: unet_precip_regression_lightning.py:193-208 / :104-117
     enc = [double_conv_ds(x, sd, "inc", training)]
     for i in range(1, 5):
         enc.append(down_ds(enc[-1], sd, f"down{i}", training))
-    att = [cbam(e, sd, f"cbam{i + 1}", training) for i, e in enumerate(enc)]
+    att = [cbam(e, sd, f"cbam{i + 1}", training) if i < n_cbams else e for i, e in enumerate(enc)]
     y = att[4]
     for i in range(1, 5):
         y = up_ds(y, att[4 - i], sd, f"up{i}", training)

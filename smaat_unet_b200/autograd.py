@@ -11,6 +11,14 @@ from . import functional as Fn
 from . import ops
 
 
+def _check_saved(ctx, what):
+    """The block Functions keep their activations in a plain dict (a dozen tensors plus scalars) that is released by the
+    first backward -- the same contract as torch's saved tensors, with torch's wording for the error."""
+    if ctx.saved is None:
+        raise RuntimeError(f"Trying to backward through the graph a second time ({what} block of smaat_unet_b200): the saved "
+                           "activations were freed by the first backward; retain_graph=True is not supported by these blocks.")
+
+
 class DoubleConvDSFn(torch.autograd.Function):
     """(DS conv => BN => ReLU) * 2 over the virtual concat [x, x1]."""
 
@@ -40,6 +48,7 @@ class DoubleConvDSFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         need = ctx.needs_input_grad
+        _check_saved(ctx, "DoubleConvDS")
         dx, dx1, pg = Fn.double_conv_bwd(ctx.mod, ctx.saved, g, need_x=need[1], need_x1=need[2])
         ctx.saved = None
         pg = [pgi if need[3 + i] else None for i, pgi in enumerate(pg)]
@@ -95,6 +104,7 @@ class CBAMFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        _check_saved(ctx, "CBAM")
         dx, pg = Fn.cbam_bwd(ctx.mod, ctx.saved, g)
         ctx.saved = None
         need = ctx.needs_input_grad

@@ -19,7 +19,7 @@ from . import _lib
 
 
 class InferenceSession:
-    def __init__(self, model, batch, in_shape, device=None, use_graph=True, slots=2):
+    def __init__(self, model, batch, in_shape, device=None, use_graph=True, slots=2, serving_fusions=True):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.model = model.to(self.device).eval()
         self.batch, self.in_shape = batch, tuple(in_shape)
@@ -30,24 +30,12 @@ class InferenceSession:
         self.static_in = torch.zeros((batch,) + self.in_shape, device=self.device, dtype=torch.float32)
         self.launches_per_forward = 0
         self.graph = None
-        with torch.cuda.device(self.device), torch.no_grad():
-            # warm-up on the compute stream: builds the folded-BN / split-weight caches (their small
-            # kernels must not be captured) and sizes the allocator
-            self.compute.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(self.compute):
-                for _ in range(2):
-                    self.static_out = self.model(self.static_in)
-            self.compute.synchronize()
-            n0 = _lib.launch_count()
-            if use_graph:
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph, stream=self.compute):
-                    self.static_out = self.model(self.static_in)
-            else:
-                with torch.cuda.stream(self.compute):
-                    self.static_out = self.model(self.static_in)
-            self.launches_per_forward = _lib.launch_count() - n0
-            self.compute.synchronize()
+        # the serving forward may fuse what plain module calls cannot express (OutConv in the last epilogue, model.py);
+        # serving_fusions=False captures exactly the reference-API call sequence
+        self._fwd = getattr(self.model, "forward_serving", None) if serving_fusions else None
+        if self._fwd is None:
+            self._fwd = self.model
+        self._capture()
         self.out_shape = tuple(self.static_out.shape)
         # staging slots (device side) so H2D of step i+1 and D2H of step i-1 overlap compute of step i
         self.slots = slots
@@ -61,13 +49,46 @@ class InferenceSession:
         self._pending = collections.deque()
         self._step = 0
 
+    def _capture(self):
+        with torch.cuda.device(self.device), torch.no_grad():
+            # warm-up on the compute stream: builds the folded-BN / split-weight caches (their small
+            # kernels must not be captured) and sizes the allocator
+            self.compute.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.compute):
+                for _ in range(2):
+                    self.static_out = self._fwd(self.static_in)
+            self.compute.synchronize()
+            n0 = _lib.launch_count()
+            if self.use_graph:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=self.compute):
+                    self.static_out = self._fwd(self.static_in)
+            else:
+                with torch.cuda.stream(self.compute):
+                    self.static_out = self._fwd(self.static_in)
+            self.launches_per_forward = _lib.launch_count() - n0
+            self.compute.synchronize()
+        # the graph has the addresses of the folded-BN / split-weight tensors baked in: keep them alive with the session.
+        # The session is a SNAPSHOT of the weights at construction; after training the model further call refresh().
+        from .modules import cached_tensors
+        self._keepalive = cached_tensors(self.model)
+
+    def refresh(self):
+        """Re-derive the weight caches and re-capture the graph: call after the model's parameters / BatchNorm statistics
+        changed (e.g. more training) -- a session is a snapshot of the weights it was built from."""
+        from . import ops
+        ops.bump_weights_generation()
+        self.model.eval()
+        self.graph = None
+        self._capture()          # static_out may be a new tensor: read it again after refresh()
+
     # -- device-resident path ---------------------------------------------------------------
     def _run(self):
         if self.graph is not None:
             self.graph.replay()
         else:
             with torch.no_grad():
-                self.static_out = self.model(self.static_in)
+                self.static_out = self._fwd(self.static_in)
 
     def forward(self, x_dev):
         """x_dev: (batch, *in_shape) CUDA tensor -> static output tensor (valid until the next call)."""

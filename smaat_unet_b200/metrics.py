@@ -112,6 +112,12 @@ class PrecipitationMetrics:
     def reset(self):
         self._totals.zero_()
 
+    def totals_snapshot(self):
+        return self._totals.clone()
+
+    def load_totals(self, snap):
+        self._totals.copy_(snap)
+
     def __getattr__(self, name):
         names = type(self)._NAMES
         if name in names and "_totals" in self.__dict__:

@@ -34,17 +34,29 @@ class SmaAt_UNet(nn.Module):
         self.outc = OutConv(64, n_classes)
 
     def forward(self, x):
+        """The reference's graph, block for block and in its call order (models/SmaAt_UNet.py:41-57): plain calls only --
+        exactly what a ``patch_reference()`` user of the unchanged reference class executes.  The max-pool fusion still
+        happens: ``cbamN(f)`` leaves MaxPool2d(2)(f) behind for the ``downN(f)`` that follows (modules.CBAM.forward)."""
         f = self.inc(x)
-        att = []
+        att = [self.cbam1(f)]
         for lvl in range(1, 5):
-            # the un-attended map feeds both cbam_l and down_l (SmaAt_UNet.py:42-50): one read of it yields the channel
-            # gate's global pools and the 2x2 max-pool (inference; with autograd / odd shapes `pooled` is None)
-            a, pooled = getattr(self, f"cbam{lvl}")(f, with_maxpool=True)
-            att.append(a)
-            f = getattr(self, f"down{lvl}")(f, pooled=pooled)
-        att.append(self.cbam5(f))
+            f = getattr(self, f"down{lvl}")(f)
+            att.append(getattr(self, f"cbam{lvl + 1}")(f))
         y = att[4]                                                  # x5Att is the decoder input
-        for i in range(3):
+        for i in range(4):
             y = getattr(self, f"up{i + 1}")(y, att[3 - i])          # attended maps are the skips
-        # up4 and outc (SmaAt_UNet.py:55-56): in inference the 1x1 OutConv rides the last DS conv's epilogue
+        return self.outc(y)
+
+    def forward_serving(self, x):
+        """Same graph with the one fusion the plain-call API cannot express: up4's last DS conv applies the 1-class OutConv
+        in its epilogue (SmaAt_UNet.py:55-56), so the 64-channel activation never reaches HBM.  Used by
+        ``engine.InferenceSession`` (inference only; falls back to the plain calls under autograd / train mode)."""
+        f = self.inc(x)
+        att = [self.cbam1(f)]
+        for lvl in range(1, 5):
+            f = getattr(self, f"down{lvl}")(f)
+            att.append(getattr(self, f"cbam{lvl + 1}")(f))
+        y = att[4]
+        for i in range(3):
+            y = getattr(self, f"up{i + 1}")(y, att[3 - i])
         return self.up4(y, att[0], outconv=self.outc)

@@ -23,7 +23,23 @@ from . import ops
 
 
 def _versions(*tensors):
-    return tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+    """Cache key for tensors derived from parameters / buffers.  ``_version`` only sees writes that go through torch
+    dispatch; our kernels (BatchNorm running statistics in smaat_bn_finalize, anything replayed from a CUDA graph)
+    write through raw pointers, so the key also carries ``ops.weights_generation()`` -- bumped by every such write
+    (ops.bn_finalize, TrainSession.step) and by every train()/eval() switch of a caching module."""
+    return (ops.weights_generation(),) + tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+
+
+class _CachingModule(nn.Module):
+    """Modules that cache tensors derived from their parameters drop those caches on every mode switch."""
+
+    def _drop_caches(self):
+        pass
+
+    def train(self, mode=True):
+        self._drop_caches()
+        ops.bump_weights_generation()
+        return super().train(mode)
 
 
 def _needs_grad(mod, *inputs):
@@ -42,7 +58,7 @@ def _no_autograd(mod, *inputs):
             "(DoubleConvDS / DownDS / UpDS / CBAM / OutConv are differentiable). Use torch.no_grad(); no PyTorch fallback is provided.")
 
 
-class DepthwiseSeparableConv(nn.Module):
+class DepthwiseSeparableConv(_CachingModule):
     """models/layers.py:34-50 -- depthwise(k x k, groups=Cin, kpl outputs per channel) then pointwise 1x1."""
 
     def __init__(self, in_channels, output_channels, kernel_size, padding=0, kernels_per_layer=1):
@@ -53,6 +69,9 @@ class DepthwiseSeparableConv(nn.Module):
         self.kernels_per_layer = kernels_per_layer
         self._wsplit = None
         self._wsplit_key = None
+
+    def _drop_caches(self):
+        self._wsplit = self._wsplit_key = None
 
     def _check(self):
         if self.depthwise.kernel_size != (3, 3) or self.depthwise.padding != (1, 1):
@@ -98,7 +117,7 @@ class DepthwiseSeparableConv(nn.Module):
         return self.run(x)
 
 
-class DoubleConvDS(nn.Module):
+class DoubleConvDS(_CachingModule):
     """models/unet_parts_depthwise_separable.py:10-39 -- (DS conv => BN => ReLU) * 2.
 
     Eval mode runs 4 kernels: dw, pw(+folded BN +ReLU), dw, pw(+folded BN +ReLU).
@@ -116,6 +135,9 @@ class DoubleConvDS(nn.Module):
             nn.BatchNorm2d(out_channels),
             nn.ReLU(inplace=True),
         )
+        self._fold = {}
+
+    def _drop_caches(self):
         self._fold = {}
 
     def _folded(self, idx):
@@ -170,6 +192,33 @@ class DoubleConvDS(nn.Module):
         return self.run(x)
 
 
+# The reference calls ``cbamN(x)`` and then ``downN(x)`` on the same un-attended map (models/SmaAt_UNet.py:42-50,
+# unet_precip_regression_lightning.py:148-157): the channel gate's global pools and the 2x2 max-pool are produced by ONE
+# read of x.  The plain-call API has no way to hand the pooled map over, so the CBAM leaves it in this one-slot stash,
+# keyed on the identity of x; DownDS takes it when (and only when) it is called on the very same tensor.
+_maxpool_stash = None
+
+
+def _tensor_key(x):
+    return (x.data_ptr(), x._version, tuple(x.shape), tuple(x.stride()), x.device.index)
+
+
+def _stash_maxpool(x, pooled):
+    global _maxpool_stash
+    _maxpool_stash = (_tensor_key(x), pooled)
+
+
+def _take_stashed_maxpool(x):
+    global _maxpool_stash
+    hit = _maxpool_stash
+    if hit is None or not isinstance(x, torch.Tensor) or not x.is_cuda:
+        return None
+    if hit[0] != _tensor_key(x):
+        return None
+    _maxpool_stash = None
+    return hit[1]
+
+
 class DownDS(nn.Module):
     """models/unet_parts_depthwise_separable.py:42-53 -- MaxPool2d(2) then DoubleConvDS."""
 
@@ -181,7 +230,10 @@ class DownDS(nn.Module):
         )
 
     def forward(self, x, pooled=None):
-        """``pooled``: MaxPool2d(2)(x) when the caller already has it (CBAM(..., with_maxpool=True))."""
+        """``pooled``: MaxPool2d(2)(x) when the caller already has it.  Called plainly (``down(x)``, as the reference does)
+        it first looks for the 2x2 max-pool the preceding ``CBAM(x)`` call left behind (see ``CBAM.forward``)."""
+        if pooled is None:
+            pooled = _take_stashed_maxpool(x)
         if pooled is None:
             if _needs_grad(self, x):
                 from .autograd import MaxPool2Fn
@@ -275,7 +327,7 @@ class ChannelAttention(nn.Module):
         return ops.cbam_scale(x, sc, ones)
 
 
-class SpatialAttention(nn.Module):
+class SpatialAttention(_CachingModule):
     """models/layers.py:114-129."""
 
     def __init__(self, kernel_size=7):
@@ -284,6 +336,9 @@ class SpatialAttention(nn.Module):
         padding = 3 if kernel_size == 7 else 1
         self.conv = nn.Conv2d(2, 1, kernel_size=kernel_size, padding=padding, bias=False)
         self.bn = nn.BatchNorm2d(1)
+        self._fold = None
+
+    def _drop_caches(self):
         self._fold = None
 
     def bn_affine(self):
@@ -316,10 +371,11 @@ class CBAM(nn.Module):
         super().__init__()
         self.channel_att = ChannelAttention(input_channels, reduction_ratio=reduction_ratio)
         self.spatial_att = SpatialAttention(kernel_size=kernel_size)
+        self.stash_maxpool = True     # False: never produce the max-pool in a plain call (e.g. no DownDS follows)
 
     def forward(self, x, out=None, with_maxpool=False):
-        """``with_maxpool=True`` returns (CBAM(x), MaxPool2d(2)(x) or None): the encoder's next DownDS pools the same map
-        (models/SmaAt_UNet.py:42-50), so the inference path produces it in the channel gate's read of x."""
+        """``with_maxpool=True`` returns (CBAM(x), MaxPool2d(2)(x) or None) explicitly; a plain ``cbam(x)`` (the reference's
+        call) returns CBAM(x) and stashes the max-pool for the DownDS that follows (models/SmaAt_UNet.py:42-50)."""
         if _needs_grad(self, x):
             from .autograd import CBAMFn
             y = CBAMFn.run(self, x)
@@ -328,11 +384,30 @@ class CBAM(nn.Module):
             from . import functional as Fn       # batch statistics for the gate's BatchNorm2d(1), no tape
             y = Fn.cbam_fwd(self, ops._dense(x, "x"))[0]
             return (y, None) if with_maxpool else y
+        # one read of x gives the global pools AND MaxPool2d(2)(x) (shape permitting); a plain call leaves the latter for
+        # the DownDS that the reference calls next on the same x
         pooled = None
-        if with_maxpool:
+        if with_maxpool or self.stash_maxpool:
             sc, pooled = self.channel_att.gate(x, with_maxpool=True)
+            if pooled is not None and not with_maxpool:
+                _stash_maxpool(x, pooled)
         else:
             sc = self.channel_att.gate(x)
         sa = self.spatial_att.gate(x, sc)
         y = ops.cbam_scale(x, sc, sa, out=out)
         return (y, pooled) if with_maxpool else y
+
+
+def cached_tensors(model):
+    """Every tensor the eval fast path derived from ``model``'s parameters (folded BatchNorm affine, tf32 hi/lo splits).
+    A CUDA graph captured over the eval forward has their addresses baked in: whoever owns the graph must keep them alive."""
+    out = []
+    for m in model.modules():
+        if isinstance(m, DepthwiseSeparableConv) and m._wsplit is not None:
+            out.extend(m._wsplit)
+        elif isinstance(m, DoubleConvDS):
+            for _, pair in m._fold.values():
+                out.extend(pair)
+        elif isinstance(m, SpatialAttention) and m._fold is not None:
+            out.append(m._fold[1])
+    return out

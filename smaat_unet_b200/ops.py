@@ -30,6 +30,21 @@ def get_pointwise_mode() -> str:
     return _pw_mode
 
 
+# ---- generation counter of "weights written behind torch's back" (see modules._versions) ----
+_weights_gen = 0
+
+
+def weights_generation() -> int:
+    return _weights_gen
+
+
+def bump_weights_generation() -> None:
+    """Call after parameters / buffers were (or may have been) written through raw pointers or a CUDA-graph replay:
+    invalidates every cache derived from them (folded BatchNorm affine, tf32 hi/lo weight splits)."""
+    global _weights_gen
+    _weights_gen += 1
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -251,6 +266,8 @@ def bn_finalize(stats, count, bn, save=False):
     track = bn.track_running_stats and bn.running_mean is not None
     if track and bn.momentum is None:
         raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative average) is not supported")
+    if track:
+        bump_weights_generation()      # running statistics are written by raw pointer: no _version bump
     _call("smaat_bn_finalize", 40 * Cn, 0, _lib.load().smaat_bn_finalize, _ptr(stats), float(count),
           _ptr(bn.weight.detach() if bn.weight is not None else None), _ptr(bn.bias.detach() if bn.bias is not None else None),
           float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1),

@@ -19,7 +19,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, ops
 from .metrics import PrecipitationMetrics, step_loss
 
 
@@ -30,6 +30,11 @@ class TrainSession:
         self.batch, self.in_shape = int(batch), tuple(in_shape)
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.use_graph = bool(use_graph)
+        if self.world > 1:
+            # replicas must start identical (what DDP / Lightning do at construction): rank 0's parameters AND buffers
+            with torch.no_grad():
+                for t in list(self.model.parameters()) + list(self.model.buffers()):
+                    dist.broadcast(t, src=0)
         self.params = [p for p in self.model.parameters() if p.requires_grad]
         # Adam(lr) as in configure_optimizers (regression_lightning.py:47-48); capturable keeps `step` on the device
         self.opt = torch.optim.Adam(self.params, lr=lr, capturable=self.use_graph, foreach=True)
@@ -78,10 +83,11 @@ class TrainSession:
                 for v in st.values():
                     if torch.is_tensor(v):
                         v.zero_()
-        self.metrics.reset()
+        self.metrics.load_totals(self._metrics_snap)      # warm-up must not disturb totals the caller already holds
 
     def _build(self, warmup):
         snap = self._snapshot()          # warm-up steps must not change the model the caller handed in
+        self._metrics_snap = self.metrics.totals_snapshot()
         cur = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(cur)
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
@@ -162,4 +168,5 @@ class TrainSession:
                 self._allreduce()
                 self._optimise()
         cur.wait_stream(self.stream)
+        ops.bump_weights_generation()    # parameters / running statistics were written by graph replay: no _version bump
         return self.loss

@@ -100,3 +100,25 @@ def test_patch_reference_rebinds_names():
     m = msu.SmaAt_UNet(12, 1)
     assert type(m.inc) is S.DoubleConvDS and type(m.cbam3) is S.CBAM and type(m.up2) is S.UpDS and type(m.outc) is S.OutConv
     assert len(m.state_dict()) == 214
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference checkout only exists in the build container")
+def test_patch_reference_reaches_the_lightning_wrappers():
+    """The Lightning wrapper classes (models/unet_precip_regression_lightning.py:86-208) import the block classes by name;
+    after patch_reference() their UNCHANGED constructors build B200 blocks and keep the reference's state_dict schema.
+    `lightning` / `torchmetrics` / `h5py` are not installed here: oracle/ref_stubs.py stands in for those imports only."""
+    from oracle import ref_stubs
+    from oracle.cases import smaat_unet_schema
+    ref_stubs.install()
+    done = S.patch_reference("/root/reference", strict=True)
+    assert "models.unet_precip_regression_lightning" in done
+    import models.unet_precip_regression_lightning as L
+    for cls, n_cbams in (("UNetDSAttention", 5), ("UNetDSAttention4CBAMs", 4), ("UNetDS", 0)):
+        m = getattr(L, cls)(hparams=ref_stubs.hparams(12, 1, 2))
+        assert type(m.inc) is S.DoubleConvDS and type(m.down4) is S.DownDS and type(m.up1) is S.UpDS and type(m.outc) is S.OutConv
+        if n_cbams:
+            assert type(m.cbam1) is S.CBAM
+        sd = m.state_dict()
+        schema = smaat_unet_schema(12, 1, 2, n_cbams=n_cbams)
+        assert set(sd) == set(schema)
+        assert all(tuple(sd[k].shape) == tuple(schema[k]) for k in schema)

@@ -55,6 +55,7 @@ _RUN = {
     "outconv": lambda c, sd, xs: torch.nn.functional.conv2d(xs[0], sd["m.conv.weight"], sd["m.conv.bias"]),
     "config1": lambda c, sd, xs: TP.cbam(TP.double_conv_ds(xs[0], sd, "conv"), sd, "cbam"),
     "unet": lambda c, sd, xs: TP.smaat_unet_forward(xs[0], sd, c.get("train", False)),
+    "lit": lambda c, sd, xs: TP.smaat_unet_forward(xs[0], sd, c.get("train", False), n_cbams=c["n_cbams"]),
 }
 
 
