@@ -103,9 +103,17 @@ int smaat_dsconv_outconv_fwd(const float* x0, int C0, int64_t x0_bstride, const 
                              const float* scale, const float* shift, const float* oc_w, const float* oc_b, float* logits,
                              int B, int H, int W, int k, int Cout, int relu, int mode, void* stream);
 
+/* Which kernel smaat_dsconv_fwd / smaat_dsconv_outconv_fwd run (same reference lines, models/layers.py:47-50): 0 = auto
+ * (default: the TMEM-operand kernel, csrc/dsconv_tmem.cu, where it applies -- k = 2, Cout <= 128, no batch statistics --
+ * else the shared-memory-operand kernel, csrc/dsconv_fused.cu), 1 = shared-memory-operand kernel only, 2 = TMEM-operand
+ * kernel only.  Process-wide; the environment variable SMAAT_DS_IMPL presets it.  For A/B measurements and tests. */
+int smaat_set_dsconv_impl(int impl);
+
 /* Debug hook: stage timers of the fused kernel's CTA 0 (16 clock64 counters accumulated over launches; layout in
  * csrc/dsconv_fused.cu).  Copies them to the HOST array `out` and clears them; synchronises the device. */
 int smaat_debug_dsconv_timing(unsigned long long* out);
+/* Same for the TMEM-operand kernel (24 counters; layout in csrc/dsconv_tmem.cu). */
+int smaat_debug_dsconv_tmem_timing(unsigned long long* out);
 
 /* 1 if this (x, w, K, Cout, P) can take the tcgen05 path (P % 4 == 0, K % 4 == 0, 16-byte aligned
  * pointers, Cout >= 8), else 0: the caller then uses SMAAT_PW_FP32_SIMT. */

@@ -547,12 +547,43 @@ static bool ds_eligible(const float* x0, int C0, int64_t bs0, const float* x1, i
   return pick_pw(H, W) != 0;
 }
 
+// second-generation kernel (dsconv_tmem.cu): A operand in tensor memory; k = 2, Cout <= 128, no batch statistics
+bool dsconv_tmem_eligible(const float* x0, int C0, int64_t bs0, const float* x1, int C1, int64_t bs1, const float* pw_w,
+                          const float* pw_w_lo, int H, int W, int k, int Cout);
+int dsconv_tmem_run(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride, const float* dw_w,
+                    const float* dw_b, const float* pw_w, const float* pw_w_lo, const float* scale, const float* shift, float* y,
+                    int64_t y_bstride, const float* oc_w, const float* oc_b, float* oc_y, int B, int H, int W, int Cout, int relu, int mode,
+                    cudaStream_t st);
+
+// 0 = auto (TMEM-operand kernel where it applies, else the shared-memory-operand kernel), 1 = shared-memory-operand kernel only,
+// 2 = TMEM-operand kernel only (shapes it does not take are refused).  SMAAT_DS_IMPL presets it.
+static std::atomic<int> g_ds_impl{-1};
+static int ds_impl() {
+  int v = g_ds_impl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("SMAAT_DS_IMPL");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 2) v = 0;
+    g_ds_impl.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 }  // namespace smaat
 
 using namespace smaat;
 
+extern "C" int smaat_set_dsconv_impl(int impl) {
+  SMAAT_REQUIRE(impl >= 0 && impl <= 2, "set_dsconv_impl: 0 = auto, 1 = shared-memory A operand, 2 = TMEM A operand");
+  g_ds_impl.store(impl, std::memory_order_relaxed);
+  return SMAAT_OK;
+}
+
 extern "C" int smaat_dsconv_eligible(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
                                      const float* pw_w, int H, int W, int k, int Cout) {
+  const int impl = ds_impl();
+  if (impl != 1 && dsconv_tmem_eligible(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, nullptr, H, W, k, Cout)) return 1;
+  if (impl == 2) return 0;
   return ds_eligible(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, nullptr, H, W, k, Cout) ? 1 : 0;
 }
 
@@ -567,7 +598,11 @@ static int dsconv_run(const float* x0, int C0, int64_t x0_bstride, const float* 
   SMAAT_REQUIRE(mode != SMAAT_PW_TF32X3 || pw_w_lo, "dsconv: TF32X3 needs pw_w_lo (see smaat_split_tf32)");
   SMAAT_REQUIRE(oc_y || y_bstride >= (int64_t)Cout * H * W, "dsconv: y batch stride too small");
   SMAAT_REQUIRE(!oc_y || (oc_w && !stats), "dsconv+outconv: needs the OutConv weight and no batch statistics");
-  if (!ds_eligible(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, pw_w_lo, H, W, k, Cout))
+  const int impl = ds_impl();
+  if (impl != 1 && !stats && dsconv_tmem_eligible(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, pw_w_lo, H, W, k, Cout))
+    return dsconv_tmem_run(x0, C0, x0_bstride, x1, C1, x1_bstride, dw_w, dw_b, pw_w, pw_w_lo, scale, shift, y, y_bstride, oc_w, oc_b, oc_y,
+                           B, H, W, Cout, relu, mode, (cudaStream_t)stream);
+  if (impl == 2 || !ds_eligible(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, pw_w_lo, H, W, k, Cout))
     return fail(SMAAT_E_UNSUPPORTED, "dsconv: shape not taken by the fused kernel (k=%d Cout=%d H=%d W=%d); use dw3x3 + pw1x1", k,
                 Cout, H, W);
   cudaStream_t st = (cudaStream_t)stream;

@@ -192,6 +192,12 @@ def set_fused_dsconv(enabled: bool) -> None:
     _fuse_ds = bool(enabled)
 
 
+def set_dsconv_impl(impl: str) -> None:
+    """Which fused DS-conv kernel runs: 'auto' (TMEM-operand kernel where it applies, else the shared-memory-operand one),
+    'smem' (round-1 kernel only) or 'tmem' (TMEM-operand kernel only; other shapes fall back to dw3x3 + pw1x1)."""
+    _lib.check(_lib.load().smaat_set_dsconv_impl({"auto": 0, "smem": 1, "tmem": 2}[impl]), "smaat_set_dsconv_impl")
+
+
 def dsconv(x, dw_weight, dw_bias, k, pw_weight, scale, shift, relu, x1=None, mode=None, w_split=None, stats=None, outconv=None):
     """Fused DepthwiseSeparableConv (layers.py:47-50) + affine (+ReLU); returns None when the fused kernel
     does not take this shape/mode (caller then runs dw3x3 + pw1x1).  ``outconv=(weight (1, Cout[,1,1]), bias or None)``

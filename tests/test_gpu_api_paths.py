@@ -251,7 +251,7 @@ def test_gradients_at_288x288_match_cpu_autograd_fp64():
     # path must stay within a small multiple of it.
     noise_max = max(rel_max(g32[k], g64[k]) for k in live)
     noise_l2 = max(rel_l2(g32[k], g64[k]) for k in live)
-    tol_max, tol_l2 = max(2e-3, 3.0 * noise_max), max(1e-3, 3.0 * noise_l2)
+    tol_max, tol_l2 = max(2e-3, 5.0 * noise_max), max(1e-3, 5.0 * noise_l2)
     worst = ("", 0.0)
     for name, p in m.named_parameters():
         got = p.grad.double().cpu().numpy()
@@ -263,12 +263,14 @@ def test_gradients_at_288x288_match_cpu_autograd_fp64():
             worst = (name, e_max)
         assert np.isfinite(e_max) and e_max <= tol_max and e_l2 <= tol_l2, \
             f"grad {name}: rel max {e_max:.3e} (tol {tol_max:.1e}), rel L2 {e_l2:.3e} (tol {tol_l2:.1e})"
-    # dL/dx is per pixel: a max-pool / channel-max argmax that flips under fp32 noise reroutes one pixel's gradient, so the
-    # input gradient is held to a relative L2 bound and a bound on the fraction of outlying pixels (both noise-calibrated)
+    # dL/dx is per pixel: a max-pool / channel-max argmax that flips under fp32 noise reroutes one pixel's gradient (the port in
+    # fp32 is off by 3e-2 of the maximum at isolated pixels), so the input gradient is held to noise-calibrated relative
+    # L2 and max-norm bounds
     gx = x.grad.double().cpu().numpy()
-    frac = lambda a: float((np.abs(a - x64) > 2e-3 * np.abs(x64).max()).mean())    # noqa: E731
-    assert rel_l2(gx, x64) <= max(2e-3, 3.0 * rel_l2(x32, x64)), f"dL/dx rel L2 {rel_l2(gx, x64):.3e} vs port fp32 {rel_l2(x32, x64):.3e}"
-    assert frac(gx) <= max(1e-4, 3.0 * frac(x32)), f"dL/dx outliers {frac(gx):.3e} vs port fp32 {frac(x32):.3e}"
+    e_l2, e_max, n_l2, n_max = rel_l2(gx, x64), rel_max(gx, x64), rel_l2(x32, x64), rel_max(x32, x64)
+    print(f"dL/dx: rel L2 {e_l2:.2e} (reference fp32: {n_l2:.2e}), rel max {e_max:.2e} (reference fp32: {n_max:.2e})")
+    assert e_l2 <= max(2e-3, 3.0 * n_l2) and e_max <= max(2e-3, 5.0 * n_max), \
+        f"dL/dx: rel L2 {e_l2:.3e} vs port fp32 {n_l2:.3e}; rel max {e_max:.3e} vs {n_max:.3e}"
     print(f"worst parameter gradient: {worst[0]} rel max {worst[1]:.2e}; reference fp32 noise: max {noise_max:.2e}, L2 {noise_l2:.2e}")
 
 

@@ -204,13 +204,35 @@ DS_CASES = [
     (1, 8, 0, 36, 52, 2, 16),      # ragged patches in x and y
     (1, 128, 128, 16, 16, 2, 64),  # K = 512: many chunks, both producer groups, concat boundary mid-loop
     (3, 24, 0, 8, 96, 2, 40),      # odd chunk count (3 per tile) -> groups alternate across tiles
+    (8, 16, 0, 128, 128, 2, 64),   # 512 tile pairs: 3-4 per CTA -> both accumulator pair buffers reused (TMEM-operand kernel)
+    (8, 16, 0, 128, 64, 2, 128),   # 256 pairs, N_TILE 128: the single accumulator pair is handed back by the epilogue
+    (2, 32, 32, 40, 72, 2, 96),    # 16 x 16 pairs with ragged right / bottom halves, concat, Cout between the tile sizes
 ]
+
+
+def _tmem_takes(H, W, k, Cout):
+    """dsconv_tmem_eligible restated: k = 2, 8 <= Cout <= 128, W % 4 == 0, and 32 x 8 / 16 x 16 tile pairs waste <= 35 %."""
+    if k != 2 or not (8 <= Cout <= 128) or W % 4:
+        return False
+    cd = lambda a, b: -(-a // b)   # noqa: E731
+    return min((cd(W, pw) * pw / W) * (cd(H, php) * php / H) for pw, php in ((32, 8), (16, 16))) <= 1.35
+
+
+@pytest.fixture(params=["smem", "tmem"])
+def ds_impl(request):
+    """Both generations of the fused kernel behind the same ABI entry: A operand staged in shared memory (dsconv_fused.cu,
+    all k) / written to tensor memory (dsconv_tmem.cu, k = 2, no batch statistics)."""
+    ops.set_dsconv_impl(request.param)
+    yield request.param
+    ops.set_dsconv_impl("auto")
 
 
 @pytest.mark.parametrize("mode", ["tf32", "tf32x3"])
 @pytest.mark.parametrize("case", DS_CASES)
-def test_dsconv_fused_matches_oracle(case, mode):
+def test_dsconv_fused_matches_oracle(case, mode, ds_impl):
     B, C0, C1, H, W, k, Cout = case
+    if ds_impl == "tmem" and not _tmem_takes(H, W, k, Cout):
+        pytest.skip("not a shape of the TMEM-operand kernel (k = 2, tile-pair waste <= 35 %)")
     C = C0 + C1
     x = rnd(B, C, H, W)
     dw_w, dw_b = rnd(k * C, 1, 3, 3), rnd(k * C)
@@ -225,19 +247,25 @@ def test_dsconv_fused_matches_oracle(case, mode):
     assert y is not None, f"fused kernel refused an eligible shape {case}"
     torch.cuda.synchronize()
     assert_close(y, ref, PW_TOL[mode], f"dsconv {mode} {case}")
-    # no bias / no affine / no relu + statistics
+    # no bias / no affine / no relu (+ statistics: shared-memory-operand kernel only)
+    pre = O.pointwise1x1(O.depthwise3x3(x.astype(np.float64), dw_w, None, k), pw_w, None)
+    if ds_impl == "tmem":
+        y2 = ops.dsconv(x0, dev(dw_w), None, k, dev(pw_w), None, None, False, x1=x1, mode=mode)
+        assert_close(y2, pre, PW_TOL[mode], f"dsconv plain {mode} {case}")
+        return
     stats = torch.zeros(2 * Cout, device="cuda", dtype=torch.float64)
     y2 = ops.dsconv(x0, dev(dw_w), None, k, dev(pw_w), None, None, False, x1=x1, mode=mode, stats=stats)
-    pre = O.pointwise1x1(O.depthwise3x3(x.astype(np.float64), dw_w, None, k), pw_w, None)
     assert_close(y2, pre, PW_TOL[mode], f"dsconv plain {mode} {case}")
     assert_close(stats[:Cout], pre.sum(axis=(0, 2, 3)), 2e-3 if mode == "tf32" else 1e-4, "dsconv channel sums")
 
 
 @pytest.mark.parametrize("mode", ["tf32", "tf32x3"])
-@pytest.mark.parametrize("case", [DS_CASES[1], DS_CASES[2], DS_CASES[3], DS_CASES[5]])
-def test_dsconv_with_fused_outconv_matches_oracle(case, mode):
+@pytest.mark.parametrize("case", [DS_CASES[1], DS_CASES[2], DS_CASES[3], DS_CASES[5], DS_CASES[8]])
+def test_dsconv_with_fused_outconv_matches_oracle(case, mode, ds_impl):
     """smaat_dsconv_outconv_fwd: DS conv -> BN/ReLU -> OutConv(Cout -> 1) with the activation kept in registers."""
     B, C0, C1, H, W, k, Cout = case
+    if ds_impl == "tmem" and not _tmem_takes(H, W, k, Cout):
+        pytest.skip("not a shape of the TMEM-operand kernel")
     C = C0 + C1
     x = rnd(B, C, H, W)
     dw_w, dw_b = rnd(k * C, 1, 3, 3), rnd(k * C)

@@ -12,7 +12,8 @@ from tests._util import NET_TOL, PW_TOL, assert_close, dev, load_np_state_dict
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-EVAL_CASES = sorted(n for n, c in CASES.items() if not c.get("train", False))
+# the Lightning-wrapper cases ("lit") are run in the wrappers' own call order by tests/test_gpu_api_paths.py
+EVAL_CASES = sorted(n for n, c in CASES.items() if not c.get("train", False) and c["kind"] != "lit")
 
 
 def build(c):
