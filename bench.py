@@ -190,6 +190,89 @@ def eager_gpu_baseline(model, xs, dev):
     return out
 
 
+def train_leg(args, dev, rank, world, S, PAR, per_gpu_batches):
+    """BASELINE configs[2] / configs[3]: the training step (forward + loss_func + metrics + backward + gradient all-reduce +
+    Adam) through train.TrainSession, host batches copied in every step.  Reported per per-GPU batch size; with N > 1 also
+    the all-reduce's own time (CUDA events around the NCCL calls), the step time with the collective switched off, and a
+    replica-consistency check (post-reduce gradients identical on all ranks and equal to the mean of the pre-reduce ones)."""
+    import torch.distributed as dist
+    from smaat_unet_b200.train import TrainSession
+    out = {"unit": "frames/s", "loss": "mse_loss(sum)/B, Adam(lr=1e-3) (regression_lightning.py:47-65)", "configs": []}
+    if world > 1:
+        out["nccl"] = {"nranks": dist.get_world_size(), "backend": dist.get_backend(), "version": ".".join(map(str, torch.cuda.nccl.version()))}
+    for B in per_gpu_batches:
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+        torch.manual_seed(0)
+        model = S.SmaAt_UNet(C_IN, 1, kernels_per_layer=2).to(dev).train()
+        try:
+            sess = TrainSession(model, B, (C_IN, SIZE, SIZE), lr=1e-3, device=dev, use_graph=not args.no_graph)
+        except torch.OutOfMemoryError:
+            out["configs"].append({"batch_per_gpu": B, "error": "out of memory"})
+            continue
+        gen = torch.Generator().manual_seed(1 + rank)
+        xs = [torch.rand((B, C_IN, SIZE, SIZE), generator=gen).pin_memory() for _ in range(2)]
+        ys = [torch.rand((B, SIZE, SIZE), generator=gen).pin_memory() for _ in range(2)]
+
+        def timed(k):
+            for i in range(3):
+                sess.step(xs[i % 2], ys[i % 2])
+            PAR.barrier(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(k):
+                sess.step(xs[i % 2], ys[i % 2])
+            e1.record()
+            PAR.barrier(dev)
+            return PAR.reduce_max(e0.elapsed_time(e1), dev) / k
+
+        k = max(5, min(args.steps, 10))
+        ms = timed(k)
+        cfg = {"batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms, "value": world * B / (ms * 1e-3),
+               "launches_per_step": sess.launches_per_step, "two_phase_backward": sess._split is not None,
+               "h2d_bytes_per_step": int(xs[0].numel() + ys[0].numel()) * 4, "max_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9}
+        if world > 1:
+            # --- replica consistency: identical parameters on all ranks after the timed steps
+            cs = sess.replica_checksums()
+            cfg["replicas_identical"] = all(c == cs[0] for c in cs)
+            # --- the collective itself: pre-reduce gradients -> expected mean (separate all-reduce of a copy) vs the session's path
+            sess.skip_allreduce = True
+            sess.set_lr(0.0)
+            sess.step(xs[0], ys[0])
+            g_local = sess.flat_grad.clone()
+            sess.skip_allreduce = False
+            expect = g_local.clone()
+            dist.all_reduce(expect, op=dist.ReduceOp.SUM)
+            expect /= world
+            sess.record_comm_timing = True
+            sess.step(xs[0], ys[0])                       # same batch, lr = 0: same local gradients, now reduced by the session
+            torch.cuda.synchronize(dev)
+            got = sess.flat_grad
+            scale = float(expect.abs().max())
+            dev_err = float((got - expect).abs().max()) / max(scale, 1e-30)
+            sums = torch.stack([got.double().sum(), got.double().abs().sum()])
+            allsums = [torch.zeros_like(sums) for _ in range(world)]
+            dist.all_gather(allsums, sums)
+            cfg["allreduce_check"] = {"post_reduce_equals_mean_of_pre_reduce_rel_err": dev_err,
+                                      "identical_on_all_ranks": all(torch.equal(a, allsums[0]) for a in allsums),
+                                      "local_differs_from_mean": bool((g_local - expect).abs().max() > 0)}
+            evs = sess.allreduce_events or []
+            cfg["allreduce"] = [{"bytes": nb, "ms": e0.elapsed_time(e1)} for e0, e1, nb in evs]
+            sess.record_comm_timing = False
+            # --- step time with the collective switched off (replicas diverge: measurement only, last thing done)
+            sess.set_lr(1e-3)
+            sess.skip_allreduce = True
+            ms_nc = timed(k)
+            sess.skip_allreduce = False
+            cfg["ms_per_step_without_allreduce"] = ms_nc
+            cfg["exposed_allreduce_ms"] = ms - ms_nc
+        out["configs"].append(cfg)
+        sess.close()
+        del sess, model, xs, ys
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -222,6 +305,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the reported-only tf32 measurement")
+    ap.add_argument("--no-train", action="store_true", help="skip the reported-only training-step leg")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: W >= 3"
 
@@ -232,6 +316,10 @@ def main():
         run_reference(args, rank)
         return
 
+    if world > 1:      # leave NCCL's init lines (comm nranks, NVLS / ring choice) in the run's stderr, never in stdout
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch.distributed as dist
     import smaat_unet_b200 as S
     from smaat_unet_b200 import parallel as PAR
@@ -428,20 +516,32 @@ def main():
                "sample": f"1 timed forward of the full batch ({n} frames 12x{SIZE}x{SIZE}) after a 1-frame warm-up; oracle/torch_port.py "
                          f"(torch CPU fp32, {threads} threads)"}
 
+    # ---------------- training step (configs[2]; configs[3] split when N > 1): reported beside the headline ----------------
+    e2e_meta = (sess.h2d_bytes_per_step, sess.d2h_bytes_per_step, sess.graph is not None)
+    train = None
+    if not args.no_train:
+        del sess
+        S.ops.bump_weights_generation()
+        batches = [B_PER_GPU] if world == 1 else sorted({B_PER_GPU, 256 // world})
+        try:
+            train = train_leg(args, dev, rank, world, S, PAR, batches)
+        except Exception as e:          # a reported-only leg must never take the headline line down
+            train = {"error": repr(e)[:300]}
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: full SmaAt-UNet forward (eval), batch=32 per GPU, 12->1ch 288x288, kernels_per_layer=2",
-                       "global_batch": B_PER_GPU * world, "pointwise": args.mode, "cuda_graph": sess.graph is not None,
+                       "global_batch": B_PER_GPU * world, "pointwise": args.mode, "cuda_graph": e2e_meta[2],
                        "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": "inputs alternate between 2 buffers; a step streams ~40 GB of activations (>> 126 MB L2)"},
             "roofline": roof, "depthwise_roofline": roof_dw, "kernels": kernels, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": sess.h2d_bytes_per_step,
-                    "d2h_bytes_per_step": sess.d2h_bytes_per_step, "ms_per_step": 1e3 * e2e_s / args.steps, "checksum": chk,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": e2e_meta[0],
+                    "d2h_bytes_per_step": e2e_meta[1], "ms_per_step": 1e3 * e2e_s / args.steps, "checksum": chk,
                     "checksum_expected": chk_expect},
-            "parity": parity, "via_reference_api": via_api, "gpu_eager_baseline": gpu_eager,
+            "parity": parity, "via_reference_api": via_api, "gpu_eager_baseline": gpu_eager, "train": train,
             "alt_mode": alt, "clocks": clocks, "gpu_launches": int(launches),
         }
         print(json.dumps(out), flush=True)

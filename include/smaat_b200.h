@@ -257,6 +257,14 @@ int smaat_mse_metrics_fwd(const float* pred, const float* target, int64_t n, flo
                           int denormalize, double* batch_acc, float* dpred, float grad_scale, void* stream);
 int smaat_metrics_commit(const double* batch_acc, double* totals, int batch_size, int denormalize, void* stream);
 
+/* ---- optimizer step (reference models/regression_lightning.py:47-48, train_SmaAtUNet.py:25: torch.optim.Adam with its
+ * defaults) over flat fp32 buffers of n floats (n % 4 == 0, 16-byte aligned; parameters, gradients, first and second moment
+ * share one layout; padding must carry zero gradients).  lr and step are DEVICE scalars (fp32; step = completed steps,
+ * incremented by the call), so a CUDA graph holding this call follows learning-rate changes.  torch's arithmetic:
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr / (1-b1^t) * m / (sqrt(v) / sqrt(1-b2^t) + eps). */
+int smaat_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr,
+                    float* step, float beta1, float beta2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,7 +51,8 @@ class DoubleConvDSFn(torch.autograd.Function):
         _check_saved(ctx, "DoubleConvDS")
         dx, dx1, pg = Fn.double_conv_bwd(ctx.mod, ctx.saved, g, need_x=need[1], need_x1=need[2])
         ctx.saved = None
-        pg = [pgi if need[3 + i] else None for i, pgi in enumerate(pg)]
+        # gradients that went straight into a session's flat bucket (functional.set_grad_sinks) bypass AccumulateGrad
+        pg = [pgi if (need[3 + i] and not Fn.is_sunk(prm)) else None for i, (pgi, prm) in enumerate(zip(pg, DoubleConvDSFn.params(ctx.mod)))]
         return (None, dx if need[1] else None, dx1 if need[2] else None, *pg)
 
 
@@ -108,7 +109,8 @@ class CBAMFn(torch.autograd.Function):
         dx, pg = Fn.cbam_bwd(ctx.mod, ctx.saved, g)
         ctx.saved = None
         need = ctx.needs_input_grad
-        return (None, dx if need[1] else None, *[p if need[2 + i] else None for i, p in enumerate(pg)])
+        prms = CBAMFn.params(ctx.mod)
+        return (None, dx if need[1] else None, *[p if (need[2 + i] and not Fn.is_sunk(prms[i])) else None for i, p in enumerate(pg)])
 
 
 class MaxPool2Fn(torch.autograd.Function):
@@ -139,12 +141,13 @@ class OutConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         x = ops._dense(x, "x")
-        ctx.save_for_backward(x, weight)
+        ctx.save_for_backward(x, weight, *([bias] if bias is not None else []))
         ctx.has_bias = bias is not None
         return ops.outconv(x, weight.detach(), bias.detach() if bias is not None else None)
 
     @staticmethod
     def backward(ctx, g):
-        x, weight = ctx.saved_tensors
-        dx, dW, db = Fn.outconv_bwd(x, weight, g, need_x=ctx.needs_input_grad[0])
-        return dx, dW, (db if ctx.has_bias else None)
+        x, weight = ctx.saved_tensors[:2]
+        bias = ctx.saved_tensors[2] if ctx.has_bias else None
+        dx, dW, db = Fn.outconv_bwd(x, weight, g, need_x=ctx.needs_input_grad[0], bias=bias)
+        return dx, (None if Fn.is_sunk(weight) else dW), (db if (ctx.has_bias and not Fn.is_sunk(bias)) else None)

@@ -87,7 +87,35 @@ from . import _lib  # noqa: E402
 _ptr, _call, _stream = ops._ptr, ops._call, ops._stream
 
 
+# Gradient sinks: a training session (train.TrainSession) owns ONE flat gradient bucket; registering its views here makes
+# every backward kernel accumulate a parameter's gradient straight into its slot of the bucket (zeroed once per step by
+# the session) -- no per-parameter zero-fill, no autograd AccumulateGrad copy, no gather before the all-reduce.
+_grad_sink = {}
+
+
+def add_grad_sinks(params, views):
+    """params[i]'s gradient is accumulated into views[i] (same shape) by the block backward passes.  Returns the keys to
+    hand to remove_grad_sinks (a parameter is identified by its storage address: it must stay alive while registered)."""
+    keys = []
+    for p, v in zip(params, views):
+        _grad_sink[p.data_ptr()] = v
+        keys.append(p.data_ptr())
+    return keys
+
+
+def remove_grad_sinks(keys):
+    for k in keys:
+        _grad_sink.pop(k, None)
+
+
+def is_sunk(p):
+    return p is not None and p.data_ptr() in _grad_sink
+
+
 def _zeros_like_param(p):
+    v = _grad_sink.get(p.data_ptr())
+    if v is not None:
+        return v
     return torch.zeros(p.shape, device=p.device, dtype=torch.float32)
 
 
@@ -236,14 +264,14 @@ def upsample2x_pad_bwd(g, in_shape):
     return dx
 
 
-def outconv_bwd(x, weight, g, need_x=True):
+def outconv_bwd(x, weight, g, need_x=True, bias=None):
     x = ops._dense(x, "x")
     g = ops._dense(g, "grad_output")
     B, Cin, H, W = x.shape
     ncls = weight.shape[0]
     dx = torch.empty_like(x) if need_x else None
     dW = _zeros_like_param(weight)
-    db = torch.zeros(ncls, device=x.device)
+    db = _zeros_like_param(bias) if bias is not None else torch.zeros(ncls, device=x.device)
     _call("smaat_outconv_bwd", 4 * B * H * W * (2 * Cin + ncls), 0, _lib.load().smaat_outconv_bwd, _ptr(g), _ptr(x), _ptr(weight.detach()),
           _ptr(dx), _ptr(dW), _ptr(db), B, Cin, ncls, H * W, _stream())
     return dx, dW, db

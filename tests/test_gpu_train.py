@@ -286,3 +286,93 @@ def test_train_session_fed_by_pinned_loader_matches_direct_batches():
     assert abs(float(l1[0]) - float(l2[0])) <= 1e-5 * abs(float(l2[0]))      # same batch, same weights
     for a, b in zip(l1[1:], l2[1:]):                                           # later steps: chaotic drift bound (see above)
         assert abs(float(a) - float(b)) <= 2e-2 * abs(float(b))
+
+
+def test_flat_adam_kernel_matches_torch_adam():
+    """smaat_adam_step (one kernel over a flat bucket, device-side lr and step count) vs torch.optim.Adam over 6 steps,
+    with a learning-rate change in the middle (ReduceLROnPlateau factor 0.1, regression_lightning.py:49-55)."""
+    from smaat_unet_b200 import _lib
+    from smaat_unet_b200.ops import _stream
+    torch.manual_seed(11)
+    n = 4096 + 64
+    p0 = torch.randn(n, device="cuda")
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    lr, step = torch.full((), 1e-3, device="cuda"), torch.zeros((), device="cuda")
+    lib = _lib.load()
+    for it in range(6):
+        g = torch.randn(n, device="cuda") * (10.0 ** (it - 3))          # a few orders of magnitude
+        if it == 3:
+            opt.param_groups[0]["lr"] = 1e-4
+            lr.fill_(1e-4)
+        p_ref.grad = g.clone()
+        opt.step()
+        _lib.check(lib.smaat_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr.data_ptr(), step.data_ptr(),
+                                       0.9, 0.999, 1e-8, _stream()), "smaat_adam_step")
+        torch.cuda.synchronize()
+        assert float(step) == it + 1
+        assert (p - p_ref.detach()).abs().max().item() <= 2e-7 * max(1.0, p_ref.detach().abs().max().item()), it
+    st = opt.state[p_ref]
+    assert_close(m, st["exp_avg"].double().cpu().numpy(), 1e-6, "exp_avg")
+    assert_close(v, st["exp_avg_sq"].double().cpu().numpy(), 1e-6, "exp_avg_sq")
+
+
+def test_train_session_lr_lives_on_the_device_and_state_dict_round_trips():
+    """a captured step must follow learning-rate changes; the optimizer state must be exportable in
+    torch.optim.Adam's schema (train_SmaAtUNet.py:85-96 checkpoints it)."""
+    from smaat_unet_b200.train import TrainSession
+    torch.manual_seed(5)
+    m = S.SmaAt_UNet(12, 1, kernels_per_layer=2).cuda()
+    sess = TrainSession(m, 2, (12, 32, 32), lr=1e-3, use_graph=True)
+    x, y = torch.rand(2, 12, 32, 32, device="cuda"), torch.rand(2, 32, 32, device="cuda")
+    w = m.outc.conv.weight
+    assert w.data_ptr() >= sess.flat_param.data_ptr() and w.grad.data_ptr() >= sess.flat_grad.data_ptr()
+    before = w.detach().clone()
+    sess.step(x, y)
+    d1 = (w.detach() - before).abs().max().item()
+    assert 0 < d1 <= 1.01e-3                       # first Adam step moves every weight by ~lr
+    sess.set_lr(0.0)
+    mid = w.detach().clone()
+    sess.step(x, y)                                # same captured graph, lr = 0: nothing may move
+    assert torch.equal(w.detach(), mid)
+    sess.set_lr(1e-5)
+    sess.step(x, y)
+    d3 = (w.detach() - mid).abs().max().item()
+    assert 0 < d3 <= 1.5e-5
+    sd = sess.optimizer_state_dict()
+    assert len(sd["state"]) == len(list(m.parameters())) and float(sd["state"][0]["step"]) == 3
+    ref = torch.optim.Adam(m.parameters(), lr=1e-3)
+    ref.load_state_dict(sd)                        # torch accepts the schema
+    assert abs(ref.param_groups[0]["lr"] - 1e-5) < 1e-12
+    m2 = S.SmaAt_UNet(12, 1, kernels_per_layer=2).cuda()
+    m2.load_state_dict(m.state_dict())
+    sess2 = TrainSession(m2, 2, (12, 32, 32), lr=1e-3, use_graph=False)
+    sess2.load_optimizer_state_dict(sd)
+    assert torch.equal(sess2.exp_avg_sq, sess.exp_avg_sq) and float(sess2.opt_step) == 3 and abs(sess2.get_lr() - 1e-5) < 1e-12
+    sess.close()
+    sess2.close()
+
+
+def test_two_phase_backward_is_verified_not_assumed():
+    """The decoder-first gradient split (train.py) is taken for SmaAt-UNet and refused -- by measurement -- for a net whose
+    decoder also reads an un-attended encoder map (UNetDSAttention4CBAMs, unet_precip_regression_lightning.py:193-208);
+    both must produce the gradients of a plain backward."""
+    from smaat_unet_b200.train import TrainSession
+    from tests.test_gpu_api_paths import RefOrderNet
+    for n_cbams, expect_split in ((5, True), (4, False)):
+        torch.manual_seed(7)
+        m = RefOrderNet(12, 1, 2, n_cbams).cuda()
+        m_ref = RefOrderNet(12, 1, 2, n_cbams).cuda().train()
+        m_ref.load_state_dict(m.state_dict())
+        sess = TrainSession(m, 2, (12, 32, 32), lr=0.0, use_graph=True)       # lr 0: weights stay comparable
+        assert (sess._split is not None) == expect_split, n_cbams
+        x, y = torch.rand(2, 12, 32, 32, device="cuda"), torch.rand(2, 32, 32, device="cuda")
+        sess.step(x, y)
+        loss = torch.nn.functional.mse_loss(m_ref(x).squeeze(1), y, reduction="sum") / 2
+        loss.backward()
+        torch.cuda.synchronize()
+        gmax = max(float(p.grad.abs().max()) for p in m_ref.parameters())
+        for (k, p), q in zip(m.named_parameters(), m_ref.parameters()):
+            assert (p.grad - q.grad).abs().max().item() <= 2e-3 * gmax, (n_cbams, k)
+        sess.close()
