@@ -257,6 +257,18 @@ int smaat_mse_metrics_fwd(const float* pred, const float* target, int64_t n, flo
                           int denormalize, double* batch_acc, float* dpred, float grad_scale, void* stream);
 int smaat_metrics_commit(const double* batch_acc, double* totals, int batch_size, int denormalize, void* stream);
 
+/* CBAM in three launches (reference models/layers.py:90-141).
+ * smaat_cbam_pool_mlp_fwd: ChannelAttention's global pools AND its shared MLP + sigmoid (layers.py:98-109): the last pooling
+ *   CTA of each image finishes the MLP; pooled != NULL also emits MaxPool2d(2)(x) from the same read (parts_ds.py:48).
+ *   counters: B ints, zero on entry and on exit.  C % 8 == 0, C <= 512, hidden <= 64 (else SMAAT_E_UNSUPPORTED).
+ * smaat_cbam_reduce_fwd (above): per-pixel channel mean / max of x * sc (layers.py:123-125).
+ * smaat_cbam_gate_scale_fwd: conv k x k (2 -> 1) + BatchNorm2d(1) affine + sigmoid AND y = (x * sc) * gate
+ *   (layers.py:126-128, :110): the gate map never reaches HBM.  W % 4 == 0, 16-byte aligned x / y (else SMAAT_E_UNSUPPORTED). */
+int smaat_cbam_pool_mlp_fwd(const float* x, float* avg, float* mx, float* pooled, const float* w1, const float* b1, const float* w2,
+                            const float* b2, float* sc, int* counters, int B, int C, int H, int W, int hidden, void* stream);
+int smaat_cbam_gate_scale_fwd(const float* pooled, const float* wsp, const float* bn_affine, const float* x, const float* sc, float* y,
+                              int64_t y_bstride, int B, int C, int H, int W, int ks, void* stream);
+
 /* ---- optimizer step (reference models/regression_lightning.py:47-48, train_SmaAtUNet.py:25: torch.optim.Adam with its
  * defaults) over flat fp32 buffers of n floats (n % 4 == 0, 16-byte aligned; parameters, gradients, first and second moment
  * share one layout; padding must carry zero gradients).  lr and step are DEVICE scalars (fp32; step = completed steps,

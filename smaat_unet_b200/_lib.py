@@ -41,6 +41,8 @@ SIGNATURES = {
     "smaat_cbam_reduce_fwd": [_p, _p, _p, _i, _i, _i, _p],
     "smaat_cbam_gate_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "smaat_cbam_scale_fwd": [_p, _p, _p, _p, _l, _i, _i, _i, _p],
+    "smaat_cbam_pool_mlp_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "smaat_cbam_gate_scale_fwd": [_p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p],
     "smaat_outconv_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     # ---- backward
     "smaat_bn_act_bwd_reduce": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],

@@ -14,11 +14,73 @@ namespace smaat {
 
 __device__ __forceinline__ float sigmoidf_acc(float v) { return 1.f / (1.f + expf(-v)); }
 
+// ---- shared MLP finished by the LAST pooling CTA of an image ------------------------------------
+// Every pooling CTA publishes its planes' (avg, max), fences, and bumps the image's counter; the CTA that completes the
+// count owns the finished (avg, max) vectors of that image and runs the two-layer MLP + sigmoid right there -- no
+// separate launch.  The counter is handed back at zero.  C <= 512, hidden <= 64 (host-checked).
+struct MlpTail {
+  const float* w1; const float* b1; const float* w2; const float* b2;   // MLP.1 (hidden x C), MLP.3 (C x hidden)
+  float* sc;            // (B, C) out
+  int* counters;        // (B) zero on entry, zero on exit
+  int C, hidden;
+};
+
+__device__ void cbam_mlp_tail(const MlpTail& t, int b, const float* avg, const float* mx) {
+  __shared__ float sa[512], sm[512], ha[64], hm[64];
+  for (int c = threadIdx.x; c < t.C; c += blockDim.x) {
+    sa[c] = __ldcg(avg + (int64_t)b * t.C + c);      // written by other CTAs: read at L2
+    sm[c] = __ldcg(mx + (int64_t)b * t.C + c);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < t.hidden; j += nw) {
+    float da = 0.f, dm = 0.f;
+    for (int c = lane; c < t.C; c += 32) {
+      const float wv = __ldg(t.w1 + (int64_t)j * t.C + c);
+      da = fmaf(wv, sa[c], da);
+      dm = fmaf(wv, sm[c], dm);
+    }
+    da = warp_sum(da);
+    dm = warp_sum(dm);
+    if (lane == 0) {
+      ha[j] = fmaxf(da + t.b1[j], 0.f);
+      hm[j] = fmaxf(dm + t.b1[j], 0.f);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < t.C; c += blockDim.x) {
+    float oa = t.b2[c], om = t.b2[c];  // second-layer bias is counted twice (layers.py:109)
+    for (int j = 0; j < t.hidden; ++j) {
+      const float wv = __ldg(t.w2 + (int64_t)c * t.hidden + j);
+      oa = fmaf(wv, ha[j], oa);
+      om = fmaf(wv, hm[j], om);
+    }
+    t.sc[(int64_t)b * t.C + c] = sigmoidf_acc(oa + om);
+  }
+}
+
+// Called by ALL threads of a pooling CTA after its planes' results are in global memory; `planes` of image b were done here.
+__device__ __forceinline__ void cbam_pool_finish(const MlpTail& t, int b, int planes, const float* avg, const float* mx) {
+  __shared__ int last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int prev = atomicAdd(t.counters + b, planes);
+    last = (prev + planes == t.C);
+    if (last) t.counters[b] = 0;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    cbam_mlp_tail(t, b, avg, mx);
+  }
+}
+
 // ---- pool ----------------------------------------------------------------------------------------
 // TPP threads cooperate on one plane; blockDim.x / TPP planes per CTA.
 template <int TPP, bool VEC>
 __global__ void __launch_bounds__(256) cbam_pool_kernel(const float* __restrict__ x, float* __restrict__ avg,
-                                                        float* __restrict__ mx, int64_t N, int P) {
+                                                        float* __restrict__ mx, int64_t N, int P, const MlpTail tail) {
   constexpr int PPB = 256 / TPP;
   const int sub = threadIdx.x / TPP;
   const int lane = threadIdx.x % TPP;
@@ -75,6 +137,11 @@ __global__ void __launch_bounds__(256) cbam_pool_kernel(const float* __restrict_
       avg[n] = S / (float)P;
       mx[n] = M;
     }
+  }
+  if (tail.sc) {   // planes of one CTA belong to one image (C % PPB == 0, host-checked)
+    const int64_t n0 = (int64_t)blockIdx.x * PPB;
+    const int planes = (int)((N - n0) < PPB ? (N - n0) : PPB);
+    cbam_pool_finish(tail, (int)(n0 / tail.C), planes, avg, mx);
   }
 }
 
@@ -334,7 +401,7 @@ __global__ void __launch_bounds__(256) cbam_scale_kernel(const float* __restrict
 template <int TPP>
 __global__ void __launch_bounds__(256) cbam_pool_maxpool_kernel(const float* __restrict__ x, float* __restrict__ avg,
                                                                 float* __restrict__ mx, float* __restrict__ pooled, int64_t N,
-                                                                int H, int W) {
+                                                                int H, int W, const MlpTail tail) {
   constexpr int PPB = 256 / TPP;
   const int sub = threadIdx.x / TPP, lane = threadIdx.x % TPP;
   const int64_t n = (int64_t)blockIdx.x * PPB + sub;
@@ -374,6 +441,91 @@ __global__ void __launch_bounds__(256) cbam_pool_maxpool_kernel(const float* __r
       mx[n] = M;
     }
   }
+  if (tail.sc) {
+    const int64_t n0 = (int64_t)blockIdx.x * PPB;
+    const int planes = (int)((N - n0) < PPB ? (N - n0) : PPB);
+    cbam_pool_finish(tail, (int)(n0 / tail.C), planes, avg, mx);
+  }
+}
+
+// ---- spatial gate + scale in one kernel: y = (x * sc) * sigmoid(BN(conv kxk(pooled))) --------------------------------------
+// The gate of a 32 x 32 pixel tile is computed exactly as cbam_gate_kernel does (staged 2-channel tile with halo), then the
+// same thread walks its 4 pixels through the CTA's slice of the channels: the 1-channel gate map never reaches HBM and
+// one launch disappears.  grid.z = B * csplit (channel slices: small planes need the parallelism).
+template <int KS>
+__global__ void __launch_bounds__(256, 4) cbam_gate_scale_kernel(const float* __restrict__ pooled, const float* __restrict__ wsp,
+                                                              const float* __restrict__ bn_affine, const float* __restrict__ x,
+                                                              const float* __restrict__ sc, float* __restrict__ y, int64_t y_bstride,
+                                                              int C, int H, int W, int csplit) {
+  constexpr int R = KS / 2;
+  constexpr int SH = GT_H + 2 * R;
+  __shared__ __align__(16) float t[2][SH][GT_P];
+  __shared__ float wk[2 * KS * KS];
+  const int b = blockIdx.z / csplit, cs = blockIdx.z - b * csplit;
+  const int x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H;
+  const int tid = threadIdx.x;
+  if (tid < 2 * KS * KS) wk[tid] = __ldg(wsp + tid);
+  const float* pb = pooled + (int64_t)b * 2 * H * W;
+  for (int i = tid; i < 2 * SH * GT_P; i += 256) {
+    const int ch = i / (SH * GT_P);
+    const int r = (i / GT_P) % SH, c = i % GT_P;
+    const int gy = y0 - R + r, gx = x0 - 4 + c;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(pb + ((int64_t)ch * H + gy) * W + gx);
+    t[ch][r][c] = v;
+  }
+  __syncthreads();
+  const int tx = tid & 7, ty = tid >> 3;
+  const float a_s = bn_affine ? __ldg(bn_affine) : 1.f;
+  const float a_t = bn_affine ? __ldg(bn_affine + 1) : 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int ch = 0; ch < 2; ++ch)
+#pragma unroll 1
+    for (int dy = 0; dy < KS; ++dy) {
+      const float* rowp = &t[ch][ty + dy][4 * tx];
+      const float4 v0 = *reinterpret_cast<const float4*>(rowp);
+      const float4 v1 = *reinterpret_cast<const float4*>(rowp + 4);
+      const float4 v2 = *reinterpret_cast<const float4*>(rowp + 8);
+      const float seg[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+      for (int dx = 0; dx < KS; ++dx) {
+        const float wv = wk[(ch * KS + dy) * KS + dx];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(wv, seg[4 - R + j + dx], acc[j]);
+      }
+    }
+  const int gy = y0 + ty, gx = x0 + 4 * tx;
+  if (gy >= H || gx >= W) return;
+  float4 g;
+  g.x = sigmoidf_acc(fmaf(acc[0], a_s, a_t)); g.y = sigmoidf_acc(fmaf(acc[1], a_s, a_t));
+  g.z = sigmoidf_acc(fmaf(acc[2], a_s, a_t)); g.w = sigmoidf_acc(fmaf(acc[3], a_s, a_t));
+  const int cper = (C + csplit - 1) / csplit;
+  const int c_lo = cs * cper, c_hi = min(C, c_lo + cper);
+  const int64_t P = (int64_t)H * W;
+  const float* xb = x + ((int64_t)b * C + c_lo) * P + (int64_t)gy * W + gx;      // W % 4 == 0 (host-checked): quads never straddle
+  float* yb = y + (int64_t)b * y_bstride + (int64_t)c_lo * P + (int64_t)gy * W + gx;
+  const float* scb = sc + (int64_t)b * C;
+  int c = c_lo;
+  for (; c + 8 <= c_hi; c += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)u * P));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float s = __ldg(scb + c + u);
+      *reinterpret_cast<float4*>(yb + (int64_t)u * P) = make_float4((v[u].x * s) * g.x, (v[u].y * s) * g.y, (v[u].z * s) * g.z, (v[u].w * s) * g.w);
+    }
+    xb += 8 * P;
+    yb += 8 * P;
+  }
+  for (; c < c_hi; ++c) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xb));
+    const float s = __ldg(scb + c);
+    *reinterpret_cast<float4*>(yb) = make_float4((v.x * s) * g.x, (v.y * s) * g.y, (v.z * s) * g.z, (v.w * s) * g.w);
+    xb += P;
+    yb += P;
+  }
 }
 
 }  // namespace smaat
@@ -390,9 +542,9 @@ extern "C" int smaat_cbam_pool_maxpool_fwd(const float* x, float* avg, float* mx
   cudaStream_t st = (cudaStream_t)stream;
   if ((int64_t)H * W >= 2048) {
     SMAAT_REQUIRE(N < (1ll << 31), "cbam_pool_maxpool: too many planes");
-    cbam_pool_maxpool_kernel<256><<<(unsigned)N, 256, 0, st>>>(x, avg, mx, pooled, N, H, W);
+    cbam_pool_maxpool_kernel<256><<<(unsigned)N, 256, 0, st>>>(x, avg, mx, pooled, N, H, W, MlpTail{});
   } else {
-    cbam_pool_maxpool_kernel<32><<<(unsigned)ceil_div64(N, 8), 256, 0, st>>>(x, avg, mx, pooled, N, H, W);
+    cbam_pool_maxpool_kernel<32><<<(unsigned)ceil_div64(N, 8), 256, 0, st>>>(x, avg, mx, pooled, N, H, W, MlpTail{});
   }
   SMAAT_LAUNCH_CHECK("smaat_cbam_pool_maxpool_fwd");
   return SMAAT_OK;
@@ -404,14 +556,73 @@ extern "C" int smaat_cbam_pool_fwd(const float* x, float* avg, float* mx, int64_
   const bool vec = (P % 4 == 0) && aligned16(x);
   if (P >= 2048) {
     SMAAT_REQUIRE(N < (1ll << 31), "cbam_pool: too many planes");
-    if (vec) cbam_pool_kernel<256, true><<<(unsigned)N, 256, 0, st>>>(x, avg, mx, N, P);
-    else cbam_pool_kernel<256, false><<<(unsigned)N, 256, 0, st>>>(x, avg, mx, N, P);
+    if (vec) cbam_pool_kernel<256, true><<<(unsigned)N, 256, 0, st>>>(x, avg, mx, N, P, MlpTail{});
+    else cbam_pool_kernel<256, false><<<(unsigned)N, 256, 0, st>>>(x, avg, mx, N, P, MlpTail{});
   } else {
     const unsigned grid = (unsigned)ceil_div64(N, 8);
-    if (vec) cbam_pool_kernel<32, true><<<grid, 256, 0, st>>>(x, avg, mx, N, P);
-    else cbam_pool_kernel<32, false><<<grid, 256, 0, st>>>(x, avg, mx, N, P);
+    if (vec) cbam_pool_kernel<32, true><<<grid, 256, 0, st>>>(x, avg, mx, N, P, MlpTail{});
+    else cbam_pool_kernel<32, false><<<grid, 256, 0, st>>>(x, avg, mx, N, P, MlpTail{});
   }
   SMAAT_LAUNCH_CHECK("smaat_cbam_pool_fwd");
+  return SMAAT_OK;
+}
+
+/* ChannelAttention's pools AND its shared MLP + sigmoid in one launch (layers.py:98-109): x (B, C, H, W) -> avg, mx (B, C),
+ * sc (B, C) = sigmoid(MLP(avg) + MLP(max)); pooled (B, C, H/2, W/2) = MaxPool2d(2)(x) when non-NULL (needs even H).  The MLP
+ * is run by the last pooling CTA of each image; `counters`: B ints, zero on entry, zero again on exit.  Needs C % 8 == 0,
+ * C <= 512, hidden <= 64; pooled additionally W % 4 == 0: SMAAT_E_UNSUPPORTED otherwise (use the separate entry points). */
+extern "C" int smaat_cbam_pool_mlp_fwd(const float* x, float* avg, float* mx, float* pooled, const float* w1, const float* b1,
+                                       const float* w2, const float* b2, float* sc, int* counters, int B, int C, int H, int W,
+                                       int hidden, void* stream) {
+  SMAAT_REQUIRE(x && avg && mx && w1 && b1 && w2 && b2 && sc && counters && B > 0 && C > 0 && H > 0 && W > 0 && hidden > 0,
+                "cbam_pool_mlp: bad arguments");
+  if (C % 8 != 0 || C > 512 || hidden > 64) return fail(SMAAT_E_UNSUPPORTED, "cbam_pool_mlp: needs C %% 8 == 0, C <= 512, hidden <= 64");
+  if (pooled && (W % 4 != 0 || H % 2 != 0 || !aligned16(x) || (reinterpret_cast<uintptr_t>(pooled) & 7u)))
+    return fail(SMAAT_E_UNSUPPORTED, "cbam_pool_mlp: the fused max-pool needs W %% 4 == 0, even H and aligned pointers (H=%d W=%d)", H, W);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t N = (int64_t)B * C;
+  const int P = H * W;
+  SMAAT_REQUIRE(N < (1ll << 31), "cbam_pool_mlp: too many planes");
+  MlpTail t{w1, b1, w2, b2, sc, counters, C, hidden};
+  if (pooled) {
+    if (P >= 2048) cbam_pool_maxpool_kernel<256><<<(unsigned)N, 256, 0, st>>>(x, avg, mx, pooled, N, H, W, t);
+    else cbam_pool_maxpool_kernel<32><<<(unsigned)ceil_div64(N, 8), 256, 0, st>>>(x, avg, mx, pooled, N, H, W, t);
+  } else {
+    const bool vec = (P % 4 == 0) && aligned16(x);
+    if (P >= 2048) {
+      if (vec) cbam_pool_kernel<256, true><<<(unsigned)N, 256, 0, st>>>(x, avg, mx, N, P, t);
+      else cbam_pool_kernel<256, false><<<(unsigned)N, 256, 0, st>>>(x, avg, mx, N, P, t);
+    } else {
+      const unsigned grid = (unsigned)ceil_div64(N, 8);
+      if (vec) cbam_pool_kernel<32, true><<<grid, 256, 0, st>>>(x, avg, mx, N, P, t);
+      else cbam_pool_kernel<32, false><<<grid, 256, 0, st>>>(x, avg, mx, N, P, t);
+    }
+  }
+  SMAAT_LAUNCH_CHECK("smaat_cbam_pool_mlp_fwd");
+  return SMAAT_OK;
+}
+
+/* SpatialAttention's conv k x k (2 -> 1) + BatchNorm2d(1) affine + sigmoid AND the final scaling in one launch
+ * (layers.py:126-128 + :110): y = (x * sc[b, c]) * sigmoid(bn(conv(pooled))).  pooled: (B, 2, H, W) from smaat_cbam_reduce_fwd,
+ * bn_affine: device [scale, shift] or NULL.  Needs W % 4 == 0 and 16-byte aligned x / y: SMAAT_E_UNSUPPORTED otherwise
+ * (use smaat_cbam_gate_fwd + smaat_cbam_scale_fwd). */
+extern "C" int smaat_cbam_gate_scale_fwd(const float* pooled, const float* wsp, const float* bn_affine, const float* x, const float* sc,
+                                         float* y, int64_t y_bstride, int B, int C, int H, int W, int ks, void* stream) {
+  SMAAT_REQUIRE(pooled && wsp && x && sc && y && B > 0 && C > 0 && H > 0 && W > 0, "cbam_gate_scale: bad arguments");
+  SMAAT_REQUIRE(ks == 3 || ks == 7, "cbam_gate_scale: kernel size must be 3 or 7 (layers.py:117), got %d", ks);
+  SMAAT_REQUIRE(y_bstride >= (int64_t)C * H * W, "cbam_gate_scale: y batch stride too small");
+  if (W % 4 != 0 || !aligned16(x) || !aligned16(y) || y_bstride % 4 != 0)
+    return fail(SMAAT_E_UNSUPPORTED, "cbam_gate_scale: needs W %% 4 == 0 and 16-byte aligned x / y");
+  const int tiles = ceil_div(W, GT_W) * ceil_div(H, GT_H);
+  // channel slices so that small planes still fill the machine (~4 CTAs per SM), at least 8 channels per slice
+  int csplit = ceil_div(4 * num_sms(), tiles * B);
+  if (csplit < 1) csplit = 1;
+  if (csplit > ceil_div(C, 8)) csplit = ceil_div(C, 8);
+  SMAAT_REQUIRE((int64_t)B * csplit <= 65535, "cbam_gate_scale: grid.z too large");
+  dim3 grid(ceil_div(W, GT_W), ceil_div(H, GT_H), B * csplit);
+  if (ks == 7) cbam_gate_scale_kernel<7><<<grid, 256, 0, (cudaStream_t)stream>>>(pooled, wsp, bn_affine, x, sc, y, y_bstride, C, H, W, csplit);
+  else cbam_gate_scale_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(pooled, wsp, bn_affine, x, sc, y, y_bstride, C, H, W, csplit);
+  SMAAT_LAUNCH_CHECK("smaat_cbam_gate_scale_fwd");
   return SMAAT_OK;
 }
 

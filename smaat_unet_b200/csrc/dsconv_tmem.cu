@@ -58,6 +58,7 @@ struct DtParams {
   float* oc_y;
   int C0, C1, H, W, Cout, relu, K;
   int px_tiles, py_tiles, total_pairs, nchunks;
+  int npass;           // output-channel passes of N_TILE channels each (Cout > 128: the depthwise work is repeated per pass)
   int timing;
 };
 
@@ -124,7 +125,7 @@ struct DtCfg {
   static constexpr int OFF_BR = ((OFF_WD + IS * WD_BYTES + 1023) / 1024) * 1024;
   static constexpr int OFF_BAR = OFF_BR + BS * BST_BYTES;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int AFF_N = 128;
+  static constexpr int AFF_N = 512;                        // epilogue affine of ALL output channels (up to 4 passes of 128)
   static constexpr int TOTAL = OFF_BAR + BAR_BYTES + 3 * AFF_N * 4 + 1024;
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
   static_assert(N_TILE <= AFF_N, "epilogue affine staging");
@@ -197,7 +198,10 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
 #define DT_ADD(idx, a, b) do { if (rec0) atomicAdd(&g_dt_timing[idx], (unsigned long long)((b) - (a))); } while (0)
 #define DT_INC(idx) do { if (rec0) atomicAdd(&g_dt_timing[idx], 1ull); } while (0)
 
-  auto pair_origin = [&](int pair, int& b, int& x0, int& y0) {
+  // work item = (pair, channel pass), pass fastest: the passes of a pair run on neighbouring SMs at the same time and
+  // share the pair's input boxes through L2
+  auto pair_origin = [&](int item, int& b, int& x0, int& y0) {
+    const int pair = item / p.npass;
     b = pair / pairs_per_img;
     const int t2 = pair - b * pairs_per_img;
     const int ty = t2 / p.px_tiles, tx = t2 - ty * p.px_tiles;
@@ -244,7 +248,8 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
     // ===== pointwise-weight ring: K-major SW128 chunks (hi rows | lo rows), one per unit, shared by both half tiles =====
     if (lane == 0) {
       uint32_t u = 0;
-      for (int j = 0; j < my_pairs; ++j)
+      for (int j = 0; j < my_pairs; ++j) {
+        const int n0 = ((blockIdx.x + j * gridDim.x) % p.npass) * N_TILE;
         for (int i = 0; i < nch; ++i, ++u) {
           const int sb = u % BS;
           DT_T(tq0);
@@ -253,9 +258,10 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
           DT_ADD(18, tq0, tq1);
           DT_INC(19);
           mbar_arrive_expect_tx(&b_full[sb], L::BST_BYTES);
-          tma_load_2d(b_base + sb * L::BST_BYTES, &map_w, &b_full[sb], i * TC_BK, 0);
-          if (X3) tma_load_2d(b_base + sb * L::BST_BYTES + L::B_BYTES, &map_wlo, &b_full[sb], i * TC_BK, 0);
+          tma_load_2d(b_base + sb * L::BST_BYTES, &map_w, &b_full[sb], i * TC_BK, n0);
+          if (X3) tma_load_2d(b_base + sb * L::BST_BYTES + L::B_BYTES, &map_wlo, &b_full[sb], i * TC_BK, n0);
         }
+      }
     }
   } else if (warp == 3) {
     // ===== depthwise-weight stager: [channel][kk][9] weights + [kk] biases -> 20-float rows (LDS.128-able) =====
@@ -364,6 +370,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
       const int pair = blockIdx.x + j * gridDim.x;
       int b, x0, y0;
       pair_origin(pair, b, x0, y0);
+      const int n0 = (pair % p.npass) * N_TILE;       // first output channel of this pass
       const uint32_t pb = (L::ACC_PAIRS == 2) ? (uint32_t)(j & 1) : 0u;
       const uint32_t use = (L::ACC_PAIRS == 2) ? (uint32_t)(j >> 1) : (uint32_t)j;
       DT_T(te0);
@@ -380,23 +387,23 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (pb * 2 + h) * N_TILE;
 #pragma unroll 1
         for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-          if (c0 >= p.Cout) break;
+          if (n0 + c0 >= p.Cout) break;
           uint32_t v[32];
           tmem_ld32(tacc + (uint32_t)c0, v);
           tmem_ld_wait();
-          const int nchn = min(32, p.Cout - c0);
-          float* yp = ypix + (int64_t)c0 * P;
+          const int nchn = min(32, p.Cout - (n0 + c0));
+          float* yp = ypix + (int64_t)(n0 + c0) * P;
 #pragma unroll
           for (int e4 = 0; e4 < 8; ++e4) {      // affine staged in shared memory: broadcast LDS.128, 4 channels at a time
-            const float4 sc4 = *reinterpret_cast<const float4*>(aff + c0 + 4 * e4);
-            const float4 sh4 = *reinterpret_cast<const float4*>(aff + L::AFF_N + c0 + 4 * e4);
+            const float4 sc4 = *reinterpret_cast<const float4*>(aff + n0 + c0 + 4 * e4);
+            const float4 sh4 = *reinterpret_cast<const float4*>(aff + L::AFF_N + n0 + c0 + 4 * e4);
             const float scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, shv[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
             float a4[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) a4[e] = fmaxf(fmaf(__uint_as_float(v[4 * e4 + e]), scv[e], shv[e]), act_lo);
             if (p.oc_y) {
               // channels past Cout: zero accumulators, identity affine, zero OutConv weight -> no mask needed
-              const float4 w4 = *reinterpret_cast<const float4*>(aff + 2 * L::AFF_N + c0 + 4 * e4);
+              const float4 w4 = *reinterpret_cast<const float4*>(aff + 2 * L::AFF_N + n0 + c0 + 4 * e4);
               oc_dot = fmaf(a4[0], w4.x, oc_dot); oc_dot = fmaf(a4[1], w4.y, oc_dot);
               oc_dot = fmaf(a4[2], w4.z, oc_dot); oc_dot = fmaf(a4[3], w4.w, oc_dot);
             } else if (pvalid) {
@@ -536,7 +543,8 @@ static int launch_dt(const CUtensorMap& m0, const CUtensorMap& m1, const CUtenso
   }
   p.px_tiles = ceil_div(p.W, PW);
   p.py_tiles = ceil_div(p.H, L::PHP);
-  const int64_t total = (int64_t)B * p.px_tiles * p.py_tiles;
+  p.npass = ceil_div(p.Cout, N_TILE);
+  const int64_t total = (int64_t)B * p.px_tiles * p.py_tiles * p.npass;
   SMAAT_REQUIRE(total < (1ll << 31), "dsconv(tmem): too many tiles");
   p.total_pairs = (int)total;
   p.nchunks = ceil_div(p.C0 + p.C1, L::CC);
@@ -565,7 +573,7 @@ static int pick_pw_pair(int H, int W) {
 bool dsconv_tmem_eligible(const float* x0, int C0, int64_t bs0, const float* x1, int C1, int64_t bs1, const float* pw_w,
                           const float* pw_w_lo, int H, int W, int k, int Cout) {
   if (k != 2) return false;
-  if (Cout > 128 || Cout < 8) return false;
+  if (Cout < 8 || Cout > 512 || (Cout > 128 && Cout % 128 != 0)) return false;   // > 128: whole passes of 128 channels
   if (W % 4 != 0 || !aligned16(x0) || bs0 % 4 != 0) return false;
   if (C1 > 0 && (!aligned16(x1) || bs1 % 4 != 0 || C0 % 16 != 0)) return false;
   const int K = k * (C0 + C1);
@@ -577,6 +585,7 @@ int dsconv_tmem_run(const float* x0, int C0, int64_t x0_bstride, const float* x1
                     const float* dw_b, const float* pw_w, const float* pw_w_lo, const float* scale, const float* shift, float* y,
                     int64_t y_bstride, const float* oc_w, const float* oc_b, float* oc_y, int B, int H, int W, int Cout, int relu, int mode,
                     cudaStream_t st) {
+  SMAAT_REQUIRE(!oc_y || Cout <= 128, "dsconv+outconv: the fused OutConv needs all Cout <= 128 channels in one pass");
   const int pw = pick_pw_pair(H, W);
   const int php = 8 * (4 / (pw / 8));
   const int n_tile = Cout > 64 ? 128 : 64;
@@ -614,7 +623,7 @@ int dsconv_tmem_run(const float* x0, int C0, int64_t x0_bstride, const float* x1
   p.dw_w = dw_w; p.dw_b = dw_b; p.scale = scale; p.shift = shift; p.y = y; p.y_bstride = y_bstride;
   p.oc_w = oc_w; p.oc_b = oc_b; p.oc_y = oc_y;
   p.C0 = C0; p.C1 = C1; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu; p.K = K;
-  p.px_tiles = p.py_tiles = p.total_pairs = p.nchunks = 0;
+  p.px_tiles = p.py_tiles = p.total_pairs = p.nchunks = p.npass = 0;
   static const int timing_on = [] { const char* e = getenv("SMAAT_DSCONV_TIMING"); return e ? atoi(e) : 0; }();
   p.timing = timing_on;
 

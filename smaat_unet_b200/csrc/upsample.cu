@@ -93,6 +93,73 @@ __global__ void __launch_bounds__(UP_THREADS) upsample2x_pad_kernel(const float*
   }
 }
 
+// ---- streaming variant (128-bit stores, no shared memory, no barriers) ------------------------------------------------
+// A thread owns 4 consecutive output columns and walks UPS_ROWS consecutive output rows of one plane.  Its 4 columns need at
+// most 4 consecutive source columns (src = dst * (W-1)/(2W-1) < dst / 2 + 1): the horizontally blended source row
+// h[j] = w_x0[j] * v[x0[j]] + w_x1[j] * v[x0[j] + 1] is kept in registers for source rows y0 and y0 + 1 and recomputed only when
+// the walk crosses into the next source row (every ~2 output rows): ~2.5 scalar loads (L1 / L2 hits: the source is 4x smaller
+// than the output and every value is read by ~4 neighbouring threads), 16 flops and one 128-bit store per 4 outputs.
+constexpr int UPS_ROWS = 8;
+__global__ void __launch_bounds__(256) upsample2x_pad_stream_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t y_bstride,
+                                                                    int C, int H, int W, int Ho, int Wo, int pad_t, int pad_l, float ry,
+                                                                    float rx, int quads, int row_groups, int64_t planes) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = (int)(t % quads);
+  const int64_t t2 = t / quads;
+  const int rg = (int)(t2 % row_groups);
+  const int64_t plane_id = t2 / row_groups;            // b * C + c
+  if (plane_id >= planes) return;
+  const int b = (int)(plane_id / C), c = (int)(plane_id - (int64_t)b * C);
+  const int ox = 4 * q;
+  // per-column source index / weights (torch: area_pixel_compute_source_index, align_corners=True); pad columns -> weight 0
+  int xi[4];
+  float wx0[4], wx1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ux = ox + j - pad_l;
+    const bool in = (ux >= 0) && (ux < 2 * W);
+    const float sx = rx * (float)max(ux, 0);
+    const int x0 = min((int)sx, W - 1);
+    const float lx = sx - (float)x0;
+    xi[j] = x0;
+    wx0[j] = in ? 1.f - lx : 0.f;
+    wx1[j] = in ? lx : 0.f;
+  }
+  const float* plane = x + ((int64_t)b * C + c) * H * W;
+  auto hrow = [&](int yy, float (&h)[4]) {
+    const float* r = plane + (int64_t)yy * W;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = wx0[j] * __ldg(r + xi[j]) + wx1[j] * __ldg(r + min(xi[j] + 1, W - 1));
+  };
+  float* dst = y + (int64_t)b * y_bstride + (int64_t)c * Ho * Wo + ox;
+  float h0[4], h1[4];
+  int cur = -1;                                        // source row held in h0 (h1 = row min(cur + 1, H - 1))
+  const int oy0 = rg * UPS_ROWS;
+#pragma unroll
+  for (int r = 0; r < UPS_ROWS; ++r) {
+    const int oy = oy0 + r;
+    if (oy >= Ho) break;
+    const int uy = oy - pad_t;
+    const bool in = (uy >= 0) && (uy < 2 * H);
+    const float sy = ry * (float)max(uy, 0);
+    const int y0 = min((int)sy, H - 1);
+    const float ly = sy - (float)y0;
+    const float w0 = in ? 1.f - ly : 0.f, w1 = in ? ly : 0.f;
+    if (y0 != cur) {
+      if (y0 == cur + 1 && cur >= 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h0[j] = h1[j];
+      } else {
+        hrow(y0, h0);
+      }
+      hrow(min(y0 + 1, H - 1), h1);
+      cur = y0;
+    }
+    *reinterpret_cast<float4*>(dst + (int64_t)oy * Wo) =
+        make_float4(w0 * h0[0] + w1 * h1[0], w0 * h0[1] + w1 * h1[1], w0 * h0[2] + w1 * h1[2], w0 * h0[3] + w1 * h1[3]);
+  }
+}
+
 }  // namespace smaat
 
 using namespace smaat;
@@ -108,6 +175,15 @@ extern "C" int smaat_upsample2x_pad_fwd(const float* x, float* y, int64_t y_bstr
   const float ry = (2 * H > 1) ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
   const float rx = (2 * W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
   const bool vec = (Wo % 4 == 0) && aligned16(y) && (y_bstride % 4 == 0);
+  if (vec) {   // Wo % 4 == 0 and aligned: every thread stores whole 128-bit quads
+    const int quads = Wo / 4, row_groups = ceil_div(Ho, UPS_ROWS);
+    const int64_t threads = (int64_t)quads * row_groups * C * B;
+    SMAAT_REQUIRE(ceil_div64(threads, 256) < (1ll << 31), "upsample2x: grid too large");
+    upsample2x_pad_stream_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, y, y_bstride, C, H, W, Ho, Wo, pad_t, pad_l, ry, rx, quads, row_groups, (int64_t)B * C);
+    SMAAT_LAUNCH_CHECK("smaat_upsample2x_pad_fwd");
+    return SMAAT_OK;
+  }
   const int tiles_x = ceil_div(Wo, UP_TX), tiles_y = ceil_div(Ho, UP_TY);
   dim3 grid(tiles_x * tiles_y, C, B);
   if (vec)

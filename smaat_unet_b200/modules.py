@@ -310,13 +310,17 @@ class ChannelAttention(nn.Module):
     def gate(self, x, with_maxpool=False):
         """sigmoid(MLP(avg) + MLP(max)) as a (B, C) tensor.  ``with_maxpool``: also return MaxPool2d(2)(x) (or None), computed
         in the same read of x as the global pools."""
+        l1, l2 = self.MLP[1], self.MLP[3]
+        one = ops.cbam_pool_mlp(x, l1.weight.detach(), l1.bias.detach(), l2.weight.detach(), l2.bias.detach(), with_maxpool=with_maxpool)
+        if one is not None:          # pools + MLP + sigmoid (+ the 2x2 max-pool) in one launch
+            sc, _, _, pooled = one
+            return (sc, pooled) if with_maxpool else sc
         pooled = None
         fused = ops.cbam_pool_maxpool(x) if with_maxpool else None
         if fused is not None:
             avg, mx, pooled = fused
         else:
             avg, mx = ops.cbam_pool(x)
-        l1, l2 = self.MLP[1], self.MLP[3]
         sc = ops.cbam_mlp(avg, mx, l1.weight.detach(), l1.bias.detach(), l2.weight.detach(), l2.bias.detach())
         return (sc, pooled) if with_maxpool else sc
 
@@ -365,7 +369,7 @@ class SpatialAttention(_CachingModule):
 
 
 class CBAM(nn.Module):
-    """models/layers.py:132-141 -- channel attention then spatial attention, 5 kernels, 4|x| of traffic."""
+    """models/layers.py:132-141 -- channel attention then spatial attention: 3 kernels, 4|x| of traffic."""
 
     def __init__(self, input_channels, reduction_ratio=16, kernel_size=7):
         super().__init__()
@@ -393,8 +397,12 @@ class CBAM(nn.Module):
                 _stash_maxpool(x, pooled)
         else:
             sc = self.channel_att.gate(x)
-        sa = self.spatial_att.gate(x, sc)
-        y = ops.cbam_scale(x, sc, sa, out=out)
+        # three launches: [pools + MLP (+ max-pool)], channel reduce, [k x k gate + scale]
+        red = ops.cbam_reduce(x, sc)
+        y = ops.cbam_gate_scale(x, sc, red, self.spatial_att.conv.weight.detach(), self.spatial_att.bn_affine(), out=out)
+        if y is None:
+            sa = ops.cbam_gate(red, self.spatial_att.conv.weight.detach(), self.spatial_att.bn_affine())
+            y = ops.cbam_scale(x, sc, sa, out=out)
         return (y, pooled) if with_maxpool else y
 
 

@@ -335,6 +335,59 @@ def cbam_pool_maxpool(x):
     return avg, mx, pooled
 
 
+_cbam_counters = {}
+
+
+def _counters(device, n):
+    """Zeroed int32 scratch (>= n entries) for the last-arriving-CTA hand-off of smaat_cbam_pool_mlp_fwd: the kernel returns
+    it at zero, so one buffer per device serves every call (stream-ordered; allocated outside any graph capture)."""
+    t = _cbam_counters.get(device)
+    if t is None or t.numel() < n:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("smaat_unet_b200: run one eager forward before capturing a CUDA graph (CBAM scratch allocation)")
+        t = torch.zeros(max(n, 256), device=device, dtype=torch.int32)
+        _cbam_counters[device] = t
+    return t
+
+
+def cbam_pool_mlp(x, w1, b1, w2, b2, with_maxpool=False):
+    """ChannelAttention gate in ONE launch: (sc, avg, mx, pooled or None); None when the shape is not taken
+    (C % 8, C > 512, hidden > 64) -- callers then use cbam_pool / cbam_pool_maxpool + cbam_mlp."""
+    x = _dense(x, "x")
+    B, Cc, H, W = x.shape
+    hidden = w1.shape[0]
+    if Cc % 8 != 0 or Cc > 512 or hidden > 64:
+        return None
+    want_pool = with_maxpool and W % 4 == 0 and H % 2 == 0
+    avg = torch.empty((B, Cc), device=x.device, dtype=torch.float32)
+    mx = torch.empty_like(avg)
+    sc = torch.empty_like(avg)
+    pooled = torch.empty((B, Cc, H // 2, W // 2), device=x.device, dtype=torch.float32) if want_pool else None
+    cnt = _counters(x.device, B)
+    _call("smaat_cbam_pool_mlp_fwd", (5 if want_pool else 4) * B * Cc * H * W, 0, _lib.load().smaat_cbam_pool_mlp_fwd, _ptr(x), _ptr(avg), _ptr(mx),
+          _ptr(pooled), _ptr(_dense(w1, "w1")), _ptr(b1), _ptr(_dense(w2, "w2")), _ptr(b2), _ptr(sc), _ptr(cnt), B, Cc, H, W, hidden, _stream())
+    return sc, avg, mx, pooled
+
+
+def cbam_gate_scale(x, sc, pooled, wsp, bn_affine, out=None):
+    """y = (x * sc) * sigmoid(bn(conv(pooled))) in one launch (layers.py:126-128, :110); None when the shape is not taken."""
+    x = _dense(x, "x")
+    B, Cc, H, W = x.shape
+    if W % 4 != 0:
+        return None
+    if out is None:
+        out = torch.empty_like(x)
+        ybs = Cc * H * W
+    else:
+        out, ybs = _nchw_bstride(out, "out")
+    if ybs % 4 != 0 or out.data_ptr() % 16 or x.data_ptr() % 16:
+        return None
+    ks = wsp.shape[-1]
+    _call("smaat_cbam_gate_scale_fwd", 4 * B * (2 * Cc + 2) * H * W, 0, _lib.load().smaat_cbam_gate_scale_fwd, _ptr(pooled), _ptr(_dense(wsp, "wsp")),
+          _ptr(bn_affine), _ptr(x), _ptr(sc), _ptr(out), ybs, B, Cc, H, W, ks, _stream())
+    return out
+
+
 def cbam_mlp(avg, mx, w1, b1, w2, b2):
     B, Cc = avg.shape
     sc = torch.empty_like(avg)

@@ -207,12 +207,15 @@ DS_CASES = [
     (8, 16, 0, 128, 128, 2, 64),   # 512 tile pairs: 3-4 per CTA -> both accumulator pair buffers reused (TMEM-operand kernel)
     (8, 16, 0, 128, 64, 2, 128),   # 256 pairs, N_TILE 128: the single accumulator pair is handed back by the epilogue
     (2, 32, 32, 40, 72, 2, 96),    # 16 x 16 pairs with ragged right / bottom halves, concat, Cout between the tile sizes
+    (2, 32, 0, 32, 32, 2, 256),    # Cout = 256: two output-channel passes of 128 over the same pairs (TMEM-operand kernel)
+    (1, 48, 16, 16, 64, 2, 512),   # Cout = 512: four passes, concat
 ]
 
 
 def _tmem_takes(H, W, k, Cout):
-    """dsconv_tmem_eligible restated: k = 2, 8 <= Cout <= 128, W % 4 == 0, and 32 x 8 / 16 x 16 tile pairs waste <= 35 %."""
-    if k != 2 or not (8 <= Cout <= 128) or W % 4:
+    """dsconv_tmem_eligible restated: k = 2, 8 <= Cout <= 128 or Cout in {256, 384, 512}, W % 4 == 0, and 32 x 8 / 16 x 16 tile
+    pairs waste <= 35 %."""
+    if k != 2 or Cout < 8 or Cout > 512 or (Cout > 128 and Cout % 128) or W % 4:
         return False
     cd = lambda a, b: -(-a // b)   # noqa: E731
     return min((cd(W, pw) * pw / W) * (cd(H, php) * php / H) for pw, php in ((32, 8), (16, 16))) <= 1.35
@@ -233,6 +236,8 @@ def test_dsconv_fused_matches_oracle(case, mode, ds_impl):
     B, C0, C1, H, W, k, Cout = case
     if ds_impl == "tmem" and not _tmem_takes(H, W, k, Cout):
         pytest.skip("not a shape of the TMEM-operand kernel (k = 2, tile-pair waste <= 35 %)")
+    if ds_impl == "smem" and Cout > 128:
+        pytest.skip("the shared-memory-operand kernel takes Cout <= 128")
     C = C0 + C1
     x = rnd(B, C, H, W)
     dw_w, dw_b = rnd(k * C, 1, 3, 3), rnd(k * C)
@@ -306,3 +311,53 @@ def test_cbam_pool_with_fused_maxpool(shape):
     ref = x.reshape(B, C, H // 2, 2, W // 2, 2).max(axis=(3, 5))
     assert np.array_equal(pooled.cpu().numpy(), ref)
     assert ops.cbam_pool_maxpool(dev(rnd(1, 2, 9, 12))) is None and ops.cbam_pool_maxpool(dev(rnd(1, 2, 8, 10))) is None
+
+
+# ------------------------------------------------------------------------------ CBAM in three launches
+@pytest.mark.parametrize("shape,hidden,with_pool", [((2, 64, 64, 64), 4, True), ((3, 128, 18, 18), 8, False), ((2, 512, 12, 16), 32, True),
+                                                    ((1, 256, 72, 72), 16, True), ((4, 8, 6, 8), 2, True)])
+def test_cbam_pool_mlp_one_launch(shape, hidden, with_pool):
+    """smaat_cbam_pool_mlp_fwd: the last pooling CTA of an image finishes the shared MLP + sigmoid (layers.py:98-109), both
+    plane-size variants, with and without the fused 2x2 max-pool; twice in a row (the counters must come back at zero)."""
+    B, C, H, W = shape
+    x = rnd(*shape)
+    w1, b1, w2, b2 = rnd(hidden, C, lo=-0.3, hi=0.3), rnd(hidden), rnd(C, hidden, lo=-0.3, hi=0.3), rnd(C)
+    x64 = x.astype(np.float64)
+    avg_r, mx_r = x64.mean(axis=(2, 3)), x64.max(axis=(2, 3))
+    mlp = lambda v: np.maximum(v @ w1.astype(np.float64).T + b1, 0) @ w2.astype(np.float64).T + b2   # noqa: E731
+    sc_r = O.sigmoid(mlp(avg_r) + mlp(mx_r))
+    for rep in range(2):
+        got = ops.cbam_pool_mlp(dev(x), dev(w1), dev(b1), dev(w2), dev(b2), with_maxpool=with_pool)
+        assert got is not None
+        sc, avg, mx, pooled = got
+        torch.cuda.synchronize()
+        assert_close(avg, avg_r, 1e-5, "avg")
+        assert np.array_equal(mx.cpu().numpy(), x.max(axis=(2, 3)))
+        assert_close(sc, sc_r, 1e-5, f"channel gate (call {rep})")
+        if with_pool and W % 4 == 0 and H % 2 == 0:
+            assert np.array_equal(pooled.cpu().numpy(), x.reshape(B, C, H // 2, 2, W // 2, 2).max(axis=(3, 5)))
+        else:
+            assert pooled is None
+        assert int(ops._counters(torch.device("cuda", torch.cuda.current_device()), B).abs().sum()) == 0
+    assert ops.cbam_pool_mlp(dev(rnd(1, 12, 8, 8)), dev(rnd(2, 12)), dev(rnd(2)), dev(rnd(12, 2)), dev(rnd(12))) is None   # C % 8
+
+
+@pytest.mark.parametrize("ks", [3, 7])
+@pytest.mark.parametrize("shape", [(2, 64, 40, 72), (1, 512, 18, 20), (3, 24, 33, 36), (1, 8, 288, 288)])
+def test_cbam_gate_scale_one_launch(shape, ks):
+    """smaat_cbam_gate_scale_fwd = smaat_cbam_gate_fwd + smaat_cbam_scale_fwd (layers.py:126-128, :110), any channel split."""
+    B, C, H, W = shape
+    x, sc = rnd(*shape), rnd(B, C, lo=0.1, hi=1.0)
+    pooled, w = rnd(B, 2, H, W), rnd(1, 2, ks, ks, lo=-0.3, hi=0.3)
+    aff = np.array([1.3, -0.2], dtype=np.float32)
+    gate = O.sigmoid(O.conv2d_same(pooled.astype(np.float64), w, ks // 2) * 1.3 - 0.2)
+    ref = x.astype(np.float64) * sc[:, :, None, None] * gate
+    y = ops.cbam_gate_scale(dev(x), dev(sc), dev(pooled), dev(w), dev(aff))
+    assert y is not None
+    assert_close(y, ref, 1e-5, f"gate+scale {shape} k{ks}")
+    # into a channel slice of a wider tensor (batch stride > C*H*W), as the virtual-concat consumers use it
+    wide = torch.zeros(B, C + 8, H, W, device="cuda")
+    ops.cbam_gate_scale(dev(x), dev(sc), dev(pooled), dev(w), dev(aff), out=wide[:, 8:])
+    assert_close(wide[:, 8:], ref, 1e-5, "gate+scale into a slice")
+    assert float(wide[:, :8].abs().max()) == 0.0
+    assert ops.cbam_gate_scale(dev(rnd(1, 8, 6, 10)), dev(rnd(1, 8)), dev(rnd(1, 2, 6, 10)), dev(w), dev(aff)) is None   # W % 4
