@@ -390,27 +390,42 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
           if (n0 + c0 >= p.Cout) break;
           uint32_t v[32];
           tmem_ld32(tacc + (uint32_t)c0, v);
+          float scv[32], shv[32];      // the affine of these 32 channels: broadcast LDS.128 while the TMEM load is in flight
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 a = *reinterpret_cast<const float4*>(aff + n0 + c0 + 4 * j4);
+            const float4 t = *reinterpret_cast<const float4*>(aff + L::AFF_N + n0 + c0 + 4 * j4);
+            scv[4 * j4] = a.x; scv[4 * j4 + 1] = a.y; scv[4 * j4 + 2] = a.z; scv[4 * j4 + 3] = a.w;
+            shv[4 * j4] = t.x; shv[4 * j4 + 1] = t.y; shv[4 * j4 + 2] = t.z; shv[4 * j4 + 3] = t.w;
+          }
           tmem_ld_wait();
-          const int nchn = min(32, p.Cout - (n0 + c0));
+          const int nchn = min(32, p.Cout - (n0 + c0));      // warp-uniform
           float* yp = ypix + (int64_t)(n0 + c0) * P;
+          if (p.oc_y) {
+            // channels past Cout: zero accumulators, identity affine, zero OutConv weight -> no mask needed
 #pragma unroll
-          for (int e4 = 0; e4 < 8; ++e4) {      // affine staged in shared memory: broadcast LDS.128, 4 channels at a time
-            const float4 sc4 = *reinterpret_cast<const float4*>(aff + n0 + c0 + 4 * e4);
-            const float4 sh4 = *reinterpret_cast<const float4*>(aff + L::AFF_N + n0 + c0 + 4 * e4);
-            const float scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, shv[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
-            float a4[4];
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(aff + 2 * L::AFF_N + n0 + c0 + 4 * j4);
+              const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) a4[e] = fmaxf(fmaf(__uint_as_float(v[4 * e4 + e]), scv[e], shv[e]), act_lo);
-            if (p.oc_y) {
-              // channels past Cout: zero accumulators, identity affine, zero OutConv weight -> no mask needed
-              const float4 w4 = *reinterpret_cast<const float4*>(aff + 2 * L::AFF_N + n0 + c0 + 4 * e4);
-              oc_dot = fmaf(a4[0], w4.x, oc_dot); oc_dot = fmaf(a4[1], w4.y, oc_dot);
-              oc_dot = fmaf(a4[2], w4.z, oc_dot); oc_dot = fmaf(a4[3], w4.w, oc_dot);
-            } else if (pvalid) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (nchn == 32 || 4 * e4 + e < nchn) yp[(int64_t)(4 * e4 + e) * P] = a4[e];
+              for (int e = 0; e < 4; ++e) {
+                const int j = 4 * j4 + e;
+                oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[j]), scv[j], shv[j]), act_lo), wv[e], oc_dot);
+              }
             }
+          } else if (nchn == 32) {
+            // hot path: FFMA, FMNMX, pointer bump, STG per channel; each store instruction of the warp = 128 (2 x 64) contiguous bytes
+            if (pvalid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                *yp = fmaxf(fmaf(__uint_as_float(v[j]), scv[j], shv[j]), act_lo);
+                yp += P;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (pvalid && j < nchn) yp[(int64_t)j * P] = fmaxf(fmaf(__uint_as_float(v[j]), scv[j], shv[j]), act_lo);
           }
         }
         if (p.oc_y && pvalid) p.oc_y[(int64_t)b * P + (int64_t)gy * p.W + gx] = oc_dot + (p.oc_b ? __ldg(p.oc_b) : 0.f);

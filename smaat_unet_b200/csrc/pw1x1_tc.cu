@@ -28,6 +28,8 @@
 // MMAs of tile i+1.  mbarriers: full/empty per smem stage, xform per stage (X3),
 // tmem_full/tmem_empty per accumulator stage; tcgen05.commit releases smem stages and
 // publishes finished accumulators.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace smaat {
@@ -43,14 +45,20 @@ struct PwTcParams {
   int tiles_m, tiles_n, total_tiles;
 };
 
-template <int N_TILE, int STAGES, bool X3>
+// ATM (TF32X3, N_TILE = 256 only): the hi / lo split of the activations is written to TENSOR MEMORY (tcgen05.st, lane = pixel)
+// and the MMAs take their A operand from TMEM: per k-chunk that removes the 32 KB the split wrote to shared memory and the
+// 48 KB the three MMA passes read back (272 -> 192 KB through the 128 B/clk port, which bounded this shape at 65 % tensor-pipe
+// activity in round 1).  TMEM: one 256-column accumulator + a 4-stage A ring of 64 columns (hi | lo).
+template <int N_TILE, int STAGES, bool X3, bool ATM = false>
 struct PwTcCfg {
+  static_assert(!ATM || (X3 && N_TILE == 256), "A-operand-in-TMEM variant: TF32X3, N_TILE = 256");
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;   // 16 KB: 4 blocks x (32 k-rows x 128 B)
   static constexpr int B_BYTES = N_TILE * TC_BK * 4;  // N_TILE rows x 128 B
-  static constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int STAGE_BYTES = ATM ? (A_BYTES + 2 * B_BYTES) : (X3 ? 2 : 1) * (A_BYTES + B_BYTES);
   static constexpr int OFF_ALO = A_BYTES;  // X3 only
-  static constexpr int OFF_B = (X3 ? 2 : 1) * A_BYTES;
+  static constexpr int OFF_B = (X3 && !ATM ? 2 : 1) * A_BYTES;
   static constexpr int OFF_BLO = OFF_B + B_BYTES;  // X3 only
+  static constexpr int AT_STAGES = 4, AT_COLS = 64;   // ATM: TMEM A ring
   static constexpr int BAR_BYTES = 512;
   static constexpr int AFF_N = 512;                                      // per-channel epilogue affine staged in smem
   static constexpr int SACC_BYTES = 4 * 2 * N_TILE * 8;                  // per-epilogue-warp fp64 BatchNorm partial sums
@@ -63,16 +71,17 @@ struct PwTcCfg {
   // adds the two halves.  N_TILE = 256 keeps three MMAs (an accumulator stage is limited to 256 of the 512 columns).
   static constexpr bool WIDE = X3 && N_TILE <= 128;
   static constexpr int ACC_COLS = WIDE ? 2 * N_TILE : N_TILE;
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;  // two accumulator stages
+  static constexpr int ACC_STAGES = ATM ? 1 : 2;
+  static constexpr int TMEM_COLS = ATM ? 512 : 2 * ACC_COLS;  // two accumulator stages (ATM: one + the A ring)
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-template <int N_TILE, int STAGES, bool X3>
-__global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
+template <int N_TILE, int STAGES, bool X3, bool ATM = false>
+__global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3, ATM>::THREADS, 1)
     pw1x1_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_wlo, const PwTcParams p) {
-  using L = PwTcCfg<N_TILE, STAGES, X3>;
+  using L = PwTcCfg<N_TILE, STAGES, X3, ATM>;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   // 1 KB alignment: swizzle atoms (8 x 128 B for the weights, 4 x 128 B for the activations).  Offset arithmetic
   // on the __shared__ array (not a uintptr_t round trip) keeps the accesses LDS/STS instead of generic LD/ST.
@@ -84,7 +93,9 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
   uint64_t* xform_bar = bars + 2 * STAGES;           // [STAGES] hi/lo split done (X3)
   uint64_t* tmem_full_bar = bars + 3 * STAGES;       // [2] accumulator complete
   uint64_t* tmem_empty_bar = bars + 3 * STAGES + 2;  // [2] accumulator drained by the epilogue
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  uint64_t* ta_full = bars + 3 * STAGES + 4;         // [AT_STAGES] ATM: hi/lo split of a chunk is in TMEM (128 arrivals)
+  uint64_t* ta_empty = ta_full + L::AT_STAGES;       // [AT_STAGES] ATM: the MMAs reading it retired
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ta_empty + L::AT_STAGES);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too
   const int lane = threadIdx.x & 31;
@@ -96,8 +107,12 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
     if (X3) tma_prefetch_desc(&map_wlo);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], ATM ? 129 : 1);       // ATM: the MMAs' commit (weights) + the 128 split threads (activations)
       mbar_init(&xform_bar[s], 128);
+    }
+    for (int s = 0; s < L::AT_STAGES; ++s) {
+      mbar_init(&ta_full[s], 128);
+      mbar_init(&ta_empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
@@ -151,16 +166,49 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
     // elected lane issues; descriptors are built once per stage and advanced by constant adds per k-step =====
     constexpr uint32_t idesc = make_idesc_tf32(N_TILE);
     constexpr uint32_t idesc_wide = make_idesc_tf32(L::WIDE ? 2 * N_TILE : N_TILE);
+    constexpr uint32_t idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     uint32_t it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t acc = tcount & 1u;
-      const uint32_t acc_ph = (tcount >> 1) & 1u;
+      const uint32_t acc = ATM ? 0u : (tcount & 1u);
+      const uint32_t acc_ph = ATM ? (tcount & 1u) : ((tcount >> 1) & 1u);
       mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * L::ACC_COLS;
       for (int i = 0; i < nk; ++i, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1u;
+        if (ATM) {
+          const int ts = it % L::AT_STAGES;
+          mbar_wait(&full_bar[s], ph);                               // weights of this chunk landed
+          mbar_wait(&ta_full[ts], (it / L::AT_STAGES) & 1u);         // activations split into TMEM
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+            const uint64_t bd0 = make_smem_desc(a_addr + L::OFF_B, 16, 1024, LAYOUT_SW128);
+            const uint64_t bl0 = make_smem_desc(a_addr + L::OFF_BLO, 16, 1024, LAYOUT_SW128);
+            const uint32_t a_hi = tmem_base + (uint32_t)L::ACC_COLS + (uint32_t)(ts * L::AT_COLS);
+            const int kc = min(TC_BK, p.K - i * TC_BK);
+            const int nmma = (kc + 7) >> 3;
+            auto tstep = [&](int kk) {
+              const uint32_t accum = (i > 0 || kk > 0) ? 1u : 0u;
+              const uint64_t bd = bd0 + (uint64_t)(kk * 2), bl = bl0 + (uint64_t)(kk * 2);
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_hi + 8u * kk), "l"(bd), "r"(idesc_ts), "r"(accum) : "memory");
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_hi + 32u + 8u * kk), "l"(bd), "r"(idesc_ts), "r"(1u) : "memory");
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_hi + 8u * kk), "l"(bl), "r"(idesc_ts), "r"(1u) : "memory");
+            };
+            if (nmma == TC_BK / 8) {
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 8; ++kk) tstep(kk);
+            } else {
+              for (int kk = 0; kk < nmma; ++kk) tstep(kk);
+            }
+            umma_commit(&empty_bar[s]);
+            umma_commit(&ta_empty[ts]);
+            if (i == nk - 1) umma_commit(&tmem_full_bar[acc]);
+          }
+          __syncwarp();
+          continue;
+        }
         mbar_wait(X3 ? &xform_bar[s] : &full_bar[s], ph);
         tc_fence_after();
         if (elect_one()) {
@@ -239,8 +287,8 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
         if (stat_n0 >= 0) flush_stats(stat_n0);
         stat_n0 = n0;
       }
-      const uint32_t acc = tcount & 1u;
-      const uint32_t acc_ph = (tcount >> 1) & 1u;
+      const uint32_t acc = ATM ? 0u : (tcount & 1u);
+      const uint32_t acc_ph = ATM ? (tcount & 1u) : ((tcount >> 1) & 1u);
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
       const int pix = tm * TC_BM + q * 32 + lane;
@@ -316,6 +364,31 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1u;
         mbar_wait(&full_bar[s], ph);
+        if (ATM) {
+          // thread = pixel = TMEM lane 32 q + lane (q = warp % 4: the lane quarter this warp may write); its 32 k values sit in
+          // the MN-major tile at a_tile_offset(k, m): for a fixed k the warp reads one 128-byte row -- conflict-free
+          const int q = warp & 3, m = q * 32 + lane;
+          const unsigned char* at = smem + s * L::STAGE_BYTES;
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float v = *reinterpret_cast<const float*>(at + a_tile_offset(k, m));
+            const float h = tf32_hi(v);
+            hi[k] = __float_as_uint(h);
+            lo[k] = __float_as_uint(v - h);
+          }
+          mbar_arrive(&empty_bar[s]);                      // the activations of this stage are in registers
+          const int ts = it % L::AT_STAGES;
+          mbar_wait(&ta_empty[ts], ((it / L::AT_STAGES) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t t0 = tmem_base + (uint32_t)L::ACC_COLS + (uint32_t)(ts * L::AT_COLS) + ((uint32_t)(q * 32) << 16);
+          tmem_st32(t0, hi);
+          tmem_st32(t0 + 32u, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          mbar_arrive(&ta_full[ts]);
+          continue;
+        }
         float4* a4 = reinterpret_cast<float4*>(smem + s * L::STAGE_BYTES);
         float4* l4 = reinterpret_cast<float4*>(smem + s * L::STAGE_BYTES + L::OFF_ALO);
 #pragma unroll
@@ -344,10 +417,10 @@ __global__ void __launch_bounds__(PwTcCfg<N_TILE, STAGES, X3>::THREADS, 1)
   }
 }
 
-template <int N_TILE, int STAGES, bool X3>
+template <int N_TILE, int STAGES, bool X3, bool ATM = false>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mwl, PwTcParams p, int B, cudaStream_t st) {
-  using L = PwTcCfg<N_TILE, STAGES, X3>;
-  auto kern = pw1x1_tc_kernel<N_TILE, STAGES, X3>;
+  using L = PwTcCfg<N_TILE, STAGES, X3, ATM>;
+  auto kern = pw1x1_tc_kernel<N_TILE, STAGES, X3, ATM>;
   static std::atomic<uint64_t> attr_mask{0};   // cudaFuncSetAttribute is per device
   if (first_use_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
@@ -403,7 +476,12 @@ int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const flo
 
   // one persistent CTA per SM: the smem ring takes ~192 KB of the 227 KB
   if (x3) {
-    if (n_tile == 256) return launch_tc<256, 2, true>(mx, mw, mwl, p, B, st);  // activations split once per 256 channels
+    if (n_tile == 256) {
+      // SMAAT_PW_ATMEM=0 keeps the round-1 variant (split written to shared memory) for A/B measurements
+      static const bool atm = [] { const char* e = getenv("SMAAT_PW_ATMEM"); return !(e && e[0] == '0'); }();
+      if (atm) return launch_tc<256, 2, true, true>(mx, mw, mwl, p, B, st);
+      return launch_tc<256, 2, true>(mx, mw, mwl, p, B, st);  // activations split once per 256 channels
+    }
     if (n_tile == 128) return launch_tc<128, 3, true>(mx, mw, mwl, p, B, st);
     return launch_tc<64, 4, true>(mx, mw, mwl, p, B, st);
   }
