@@ -269,6 +269,18 @@ int smaat_cbam_pool_mlp_fwd(const float* x, float* avg, float* mx, float* pooled
 int smaat_cbam_gate_scale_fwd(const float* pooled, const float* wsp, const float* bn_affine, const float* x, const float* sc, float* y,
                               int64_t y_bstride, int B, int C, int H, int W, int ks, void* stream);
 
+/* ---- UpDS(bilinear=False): nn.ConvTranspose2d(in, in // 2, 2, stride=2) + F.pad (reference
+ * models/unet_parts_depthwise_separable.py:72-73, 76-81).  Kernel = stride = 2: no overlapping taps, so the transposed conv is ONE
+ * pointwise GEMM Cin -> 4 Cout packed channels (smaat_pw1x1_fwd on the repacked weight) followed by a 2x2 pixel shuffle.
+ *   smaat_convt2x2_pack_weight:  W (Cin, Cout, 2, 2) -> Wp (4 Cout, Cin), row (2 dy + dx) Cout + o
+ *   smaat_pixel_shuffle2_pad_fwd: t (B, 4 Cout, H, W) [+ bias (Cout) or NULL] -> y (B, Cout, Ho, Wo), zero pad frame
+ *   smaat_pixel_shuffle2_pad_bwd: the gather transpose; smaat_convt2x2_unpack_wgrad ACCUMULATES dWp / dbp into dW / db. */
+int smaat_convt2x2_pack_weight(const float* w, float* wp, int Cin, int Cout, void* stream);
+int smaat_convt2x2_unpack_wgrad(const float* dwp, const float* dbp, float* dw, float* db, int Cin, int Cout, void* stream);
+int smaat_pixel_shuffle2_pad_fwd(const float* t, const float* bias, float* y, int64_t y_bstride, int B, int Cout, int H, int W, int Ho,
+                                 int Wo, void* stream);
+int smaat_pixel_shuffle2_pad_bwd(const float* g, int64_t g_bstride, float* dt, int B, int Cout, int H, int W, int Ho, int Wo, void* stream);
+
 /* ---- optimizer step (reference models/regression_lightning.py:47-48, train_SmaAtUNet.py:25: torch.optim.Adam with its
  * defaults) over flat fp32 buffers of n floats (n % 4 == 0, 16-byte aligned; parameters, gradients, first and second moment
  * share one layout; padding must carry zero gradients).  lr and step are DEVICE scalars (fp32; step = completed steps,

@@ -126,6 +126,10 @@ CASES = {
     "down_eval": dict(kind="down", cin=8, cout=16, k=2, x=(2, 8, 13, 18), seed=31, train=False),
     "up_eval_even": dict(kind="up", cin=32, cout=8, k=2, x=(2, 16, 6, 8), skip=(2, 16, 12, 16), seed=41, train=False),
     "up_eval_pad": dict(kind="up", cin=32, cout=8, k=1, x=(1, 16, 4, 6), skip=(1, 16, 9, 13), seed=42, train=False),
+    # UpDS(bilinear=False): ConvTranspose2d(in, in // 2, 2, 2) upsampling (parts_ds.py:72-73); x has `cin` channels, the skip cin // 2
+    "up_convt_even": dict(kind="up", cin=32, cout=8, k=2, x=(2, 32, 6, 8), skip=(2, 16, 12, 16), seed=43, train=False, bilinear=False),
+    "up_convt_pad": dict(kind="up", cin=16, cout=8, k=1, x=(1, 16, 4, 6), skip=(1, 8, 9, 13), seed=44, train=False, bilinear=False),
+    "up_convt_train": dict(kind="up", cin=16, cout=8, k=2, x=(2, 16, 4, 4), skip=(2, 8, 8, 8), seed=45, train=True, bilinear=False),
     "cbam_k7_eval": dict(kind="cbam", c=32, r=16, ks=7, x=(2, 32, 14, 10), seed=51, train=False),
     "cbam_k3_eval": dict(kind="cbam", c=64, r=8, ks=3, x=(1, 64, 9, 9), seed=52, train=False),
     "cbam_k7_train": dict(kind="cbam", c=32, r=16, ks=7, x=(3, 32, 12, 12), seed=53, train=True),
@@ -154,6 +158,10 @@ def case_schema(c):
     if kind == "down":
         return double_conv_ds_schema("m.maxpool_conv.1", c["cin"], c["cout"], None, c["k"])
     if kind == "up":
+        if not c.get("bilinear", True):      # parts_ds.py:72-73: ConvTranspose2d(in, in // 2, 2, 2) + DoubleConvDS(in, out)
+            s = {"m.up.weight": (c["cin"], c["cin"] // 2, 2, 2), "m.up.bias": (c["cin"] // 2,)}
+            s.update(double_conv_ds_schema("m.conv", c["cin"], c["cout"], None, c["k"]))
+            return s
         return double_conv_ds_schema("m.conv", c["cin"], c["cout"], c["cin"] // 2, c["k"])
     if kind == "cbam":
         return cbam_schema("m", c["c"], c["r"], c["ks"])

@@ -50,7 +50,7 @@ def build_reference_module(c):
     if kind == "down":
         return Wrap(DownDS(c["cin"], c["cout"], kernels_per_layer=c["k"]))
     if kind == "up":
-        return Wrap(UpDS(c["cin"], c["cout"], True, kernels_per_layer=c["k"]))
+        return Wrap(UpDS(c["cin"], c["cout"], c.get("bilinear", True), kernels_per_layer=c["k"]))
     if kind == "cbam":
         return Wrap(CBAM(c["c"], reduction_ratio=c["r"], kernel_size=c["ks"]))
     if kind == "outconv":

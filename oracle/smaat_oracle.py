@@ -201,9 +201,26 @@ def down_ds(x, sd, prefix, k, training=False):
     return double_conv_ds(maxpool2(x), sd, prefix + ".maxpool_conv.1", k, training)
 
 
+def conv_transpose2x2(x, w, b):
+    """nn.ConvTranspose2d(Cin, Cout, kernel_size=2, stride=2) (parts_ds.py:72): w (Cin, Cout, 2, 2);
+    y[b, o, 2i + dy, 2j + dx] = bias[o] + sum_c x[b, c, i, j] * w[c, o, dy, dx] -- no overlapping taps."""
+    B, _, H, W = x.shape
+    Cout = w.shape[1]
+    y = np.zeros((B, Cout, 2 * H, 2 * W), dtype=x.dtype)
+    for dy in range(2):
+        for dx in range(2):
+            y[:, :, dy::2, dx::2] = np.einsum("bcij,co->boij", x, w[:, :, dy, dx].astype(x.dtype))
+    return y + b.astype(x.dtype)[None, :, None, None]
+
+
 def up_ds(x_low, x_skip, sd, prefix, k, training=False):
-    """UpDS bilinear branch (parts_ds.py:56-86): upsample x2, pad to skip, cat([skip, up]), DoubleConvDS."""
-    up = pad_to(upsample_bilinear2x(x_low), x_skip.shape[2], x_skip.shape[3])
+    """UpDS (parts_ds.py:56-86): upsample x2 (bilinear, or ConvTranspose2d when the state_dict holds `up.weight`), pad to skip,
+    cat([skip, up]), DoubleConvDS."""
+    if prefix + ".up.weight" in sd:
+        up = conv_transpose2x2(x_low, sd[prefix + ".up.weight"], sd[prefix + ".up.bias"])
+    else:
+        up = upsample_bilinear2x(x_low)
+    up = pad_to(up, x_skip.shape[2], x_skip.shape[3])
     return double_conv_ds(np.concatenate([x_skip, up], axis=1), sd, prefix + ".conv", k, training)
 
 

@@ -45,8 +45,11 @@ def down_ds(x, sd, p, training=False):
 
 
 def up_ds(x_low, x_skip, sd, p, training=False):
-    # parts_ds.py:75-86 (bilinear branch)
-    up = F.interpolate(x_low, scale_factor=2, mode="bilinear", align_corners=True)
+    # parts_ds.py:75-86 (bilinear branch; ConvTranspose2d branch :72-73 when the state_dict holds up.weight)
+    if p + ".up.weight" in sd:
+        up = F.conv_transpose2d(x_low, sd[p + ".up.weight"], sd[p + ".up.bias"], stride=2)
+    else:
+        up = F.interpolate(x_low, scale_factor=2, mode="bilinear", align_corners=True)
     dY, dX = x_skip.shape[2] - up.shape[2], x_skip.shape[3] - up.shape[3]
     up = F.pad(up, [dX // 2, dX - dX // 2, dY // 2, dY - dY // 2])
     return double_conv_ds(torch.cat([x_skip, up], dim=1), sd, p + ".conv", training)

@@ -63,6 +63,10 @@ SIGNATURES = {
     "smaat_cbam_mlp_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "smaat_mse_metrics_fwd": [_p, _p, _l, _f, _f, _i, _p, _p, _f, _p],
     "smaat_metrics_commit": [_p, _p, _i, _i, _p],
+    "smaat_convt2x2_pack_weight": [_p, _p, _i, _i, _p],
+    "smaat_convt2x2_unpack_wgrad": [_p, _p, _p, _p, _i, _i, _p],
+    "smaat_pixel_shuffle2_pad_fwd": [_p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
+    "smaat_pixel_shuffle2_pad_bwd": [_p, _l, _p, _i, _i, _i, _i, _i, _i, _p],
     "smaat_adam_step": [_p, _p, _p, _p, _l, _p, _p, _f, _f, _f, _p],
 }
 _SPECIAL = {

@@ -137,6 +137,42 @@ class Upsample2xPadFn(torch.autograd.Function):
         return Fn.upsample2x_pad_bwd(g, ctx.in_shape), None, None
 
 
+class ConvT2x2PadFn(torch.autograd.Function):
+    """nn.ConvTranspose2d(Cin, Cout, 2, stride=2) + F.pad to (Ho, Wo) (parts_ds.py:72-73, 76-81): one pointwise GEMM to the
+    4 Cout packed taps + a pixel shuffle; backward = the gather transpose + the pointwise backward + the weight un-pack."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, Ho, Wo, wp, w_split):
+        x = ops._dense(x, "x")
+        Cout = weight.shape[1]
+        t = ops.pw1x1(x, wp, None, None, False, w_split=w_split)
+        ctx.save_for_backward(x, weight, wp, *([bias] if bias is not None else []))
+        ctx.has_bias, ctx.out_hw = bias is not None, (Ho, Wo)
+        return ops.pixel_shuffle2_pad(t, bias.detach() if bias is not None else None, Cout, Ho, Wo)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        x, weight, wp = ctx.saved_tensors[:3]
+        bias = ctx.saved_tensors[3] if ctx.has_bias else None
+        B, Cin, H, W = x.shape
+        Cout = weight.shape[1]
+        Ho, Wo = ctx.out_hw
+        lib = _lib.load()
+        g, gbs = ops._nchw_bstride(g, "grad_output")
+        dt = torch.empty((B, 4 * Cout, H, W), device=x.device, dtype=torch.float32)
+        ops._call("smaat_pixel_shuffle2_pad_bwd", 8 * dt.numel(), 0, lib.smaat_pixel_shuffle2_pad_bwd, ops._ptr(g), gbs, ops._ptr(dt), B, Cout, H, W, Ho,
+                  Wo, ops._stream())
+        dwp = torch.zeros_like(wp)
+        dbp = torch.zeros(4 * Cout, device=x.device, dtype=torch.float32)
+        dx = Fn.pw_bwd(dt, x, wp, dwp, dbp, need_input=ctx.needs_input_grad[0])
+        dW = Fn._zeros_like_param(weight)
+        db = Fn._zeros_like_param(bias) if bias is not None else None
+        ops._call("smaat_convt2x2_unpack_wgrad", 8 * dwp.numel(), 0, lib.smaat_convt2x2_unpack_wgrad, ops._ptr(dwp), ops._ptr(dbp), ops._ptr(dW), ops._ptr(db),
+                  Cin, Cout, ops._stream())
+        return (dx, None if Fn.is_sunk(weight) else dW, (db if (bias is not None and not Fn.is_sunk(bias)) else None), None, None, None, None)
+
+
 class OutConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):

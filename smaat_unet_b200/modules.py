@@ -243,10 +243,12 @@ class DownDS(nn.Module):
         return self.maxpool_conv[1].run(pooled)
 
 
-class UpDS(nn.Module):
+class UpDS(_CachingModule):
     """models/unet_parts_depthwise_separable.py:56-86 -- upsample x2, pad to the skip, concat, DoubleConvDS.
 
     The concat is never materialised: the first depthwise kernel reads [skip, up] as a virtual concat.
+    ``bilinear=False`` (ConvTranspose2d(in, in // 2, 2, stride=2), :72-73): kernel = stride, so the transposed conv is one
+    tcgen05 pointwise GEMM to the 4 packed taps + a pixel shuffle (csrc/convt.cu).
     """
 
     def __init__(self, in_channels, out_channels, bilinear=True, kernels_per_layer=1):
@@ -258,11 +260,37 @@ class UpDS(nn.Module):
         else:
             self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
             self.conv = DoubleConvDS(in_channels, out_channels, kernels_per_layer=kernels_per_layer)
+        self._packed = None
+
+    def _drop_caches(self):
+        self._packed = None
+
+    def _packed_weight(self):
+        """((4 Cout, Cin) GEMM matrix of the transposed conv, its tf32 (hi, lo) split or None); cached on the weight's version."""
+        w = self.up.weight
+        key = (_versions(w), ops.get_pointwise_mode())
+        in_train_capture = self.training and torch.cuda.is_current_stream_capturing()
+        if in_train_capture or self._packed is None or self._packed[0] != key:
+            with torch.no_grad():
+                wp = ops.convt2x2_pack_weight(w.detach())
+                split = ops.split_tf32(wp) if ops.get_pointwise_mode() == "tf32x3" else None
+            self._packed = (None if in_train_capture else key, wp, split)
+        return self._packed[1], self._packed[2]
+
+    def _up_transposed(self, x1, Ho, Wo):
+        up = self.up
+        if (up.kernel_size, up.stride, up.padding, up.output_padding, up.dilation, up.groups) != ((2, 2), (2, 2), (0, 0), (0, 0), (1, 1), 1):
+            raise NotImplementedError("UpDS: only the reference's ConvTranspose2d(kernel_size=2, stride=2) is implemented (parts_ds.py:72)")
+        wp, split = self._packed_weight()
+        if _needs_grad(up, x1):
+            from .autograd import ConvT2x2PadFn
+            return ConvT2x2PadFn.apply(x1, up.weight, up.bias, Ho, Wo, wp, split)
+        t = ops.pw1x1(x1, wp, None, None, False, w_split=split)
+        return ops.pixel_shuffle2_pad(t, up.bias.detach() if up.bias is not None else None, up.out_channels, Ho, Wo)
 
     def forward(self, x1, x2, outconv=None):
         if not self.bilinear:
-            raise NotImplementedError("UpDS(bilinear=False) (ConvTranspose2d upsampling, parts_ds.py:72-73) is not "
-                                      "implemented in this build; the SmaAt-UNet configs use bilinear=True")
+            return self.conv.run(x2, x1=self._up_transposed(x1, x2.shape[2], x2.shape[3]), outconv=outconv)
         if torch.is_grad_enabled() and x1.requires_grad:
             from .autograd import Upsample2xPadFn
             up = Upsample2xPadFn.apply(x1, x2.shape[2], x2.shape[3])

@@ -312,6 +312,26 @@ def upsample2x_pad(x, Ho, Wo):
     return y
 
 
+def convt2x2_pack_weight(w):
+    """ConvTranspose2d(k=2, s=2) weight (Cin, Cout, 2, 2) -> the pointwise GEMM's (4 Cout, Cin) matrix (csrc/convt.cu)."""
+    w = _dense(w, "up.weight")
+    Cin, Cout = w.shape[0], w.shape[1]
+    wp = torch.empty((4 * Cout, Cin), device=w.device, dtype=torch.float32)
+    _call("smaat_convt2x2_pack_weight", 8 * w.numel(), 0, _lib.load().smaat_convt2x2_pack_weight, _ptr(w), _ptr(wp), Cin, Cout, _stream())
+    return wp
+
+
+def pixel_shuffle2_pad(t, bias, Cout, Ho, Wo):
+    """(B, 4 Cout, H, W) packed taps -> (B, Cout, Ho, Wo): 2x2 pixel shuffle + bias + F.pad frame (parts_ds.py:76-81)."""
+    t = _dense(t, "t")
+    B, C4, H, W = t.shape
+    assert C4 == 4 * Cout
+    y = torch.empty((B, Cout, Ho, Wo), device=t.device, dtype=torch.float32)
+    _call("smaat_pixel_shuffle2_pad_fwd", 4 * B * Cout * (4 * H * W + Ho * Wo), 0, _lib.load().smaat_pixel_shuffle2_pad_fwd, _ptr(t), _ptr(bias), _ptr(y),
+          Cout * Ho * Wo, B, Cout, H, W, Ho, Wo, _stream())
+    return y
+
+
 def cbam_pool(x):
     x = _dense(x, "x")
     B, Cc, H, W = x.shape

@@ -65,7 +65,7 @@ def test_block_schemas_match():
         elif kind == "down":
             m = S.DownDS(c["cin"], c["cout"], kernels_per_layer=c["k"])
         elif kind == "up":
-            m = S.UpDS(c["cin"], c["cout"], True, kernels_per_layer=c["k"])
+            m = S.UpDS(c["cin"], c["cout"], c.get("bilinear", True), kernels_per_layer=c["k"])
         elif kind == "cbam":
             m = S.CBAM(c["c"], reduction_ratio=c["r"], kernel_size=c["ks"])
         elif kind == "outconv":

@@ -25,7 +25,7 @@ def build(c):
     if kind == "down":
         return S.DownDS(c["cin"], c["cout"], kernels_per_layer=c["k"]), "m."
     if kind == "up":
-        return S.UpDS(c["cin"], c["cout"], True, kernels_per_layer=c["k"]), "m."
+        return S.UpDS(c["cin"], c["cout"], c.get("bilinear", True), kernels_per_layer=c["k"]), "m."
     if kind == "cbam":
         return S.CBAM(c["c"], reduction_ratio=c["r"], kernel_size=c["ks"]), "m."
     if kind == "outconv":
@@ -78,8 +78,10 @@ def test_standalone_attention_modules():
 
 
 def test_unsupported_requests_are_refused_loudly_not_silently_wrong():
-    with pytest.raises(NotImplementedError):          # ConvTranspose2d upsampling branch (parts_ds.py:72-73)
-        S.UpDS(8, 4, bilinear=False).cuda().eval()(torch.zeros(1, 4, 4, 4, device="cuda"), torch.zeros(1, 4, 8, 8, device="cuda"))
+    up = S.UpDS(8, 4, bilinear=False).cuda().eval()   # only the reference's ConvTranspose2d(kernel_size=2, stride=2) exists (parts_ds.py:72)
+    up.up = torch.nn.ConvTranspose2d(8, 4, kernel_size=3, stride=2).cuda()
+    with pytest.raises(NotImplementedError), torch.no_grad():
+        up(torch.zeros(1, 8, 4, 4, device="cuda"), torch.zeros(1, 4, 8, 8, device="cuda"))
     with pytest.raises(NotImplementedError):          # standalone attention halves have no autograd node (CBAM does)
         S.ChannelAttention(16).cuda()(torch.zeros(1, 16, 8, 8, device="cuda"))
     with pytest.raises(NotImplementedError):          # only the reference's 3x3 / padding=1 depthwise exists

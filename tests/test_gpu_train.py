@@ -76,6 +76,7 @@ def _cpu_reference(kind, c, sd_np, xs_np, train, R, dtype=torch.float64):
 
 
 GRAD_CASES = ["dsconv_k1", "dsconv_k2", "dsconv_k3", "doubleconv_eval", "doubleconv_mid_eval", "doubleconv_train", "down_eval", "up_eval_even", "up_eval_pad",
+              "up_convt_even", "up_convt_pad", "up_convt_train",
               "cbam_k7_eval", "cbam_k3_eval", "cbam_k7_train", "outconv", "unet_12_1_k2_32", "unet_12_1_k2_train", "unet_3_5_k1_48"]
 
 
