@@ -80,8 +80,8 @@ def test_no_cpu_fallback_fails_loudly():
     m = S.SmaAt_UNet(12, 1).eval()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 12, 32, 32))
-    with pytest.raises(NotImplementedError):
-        S.UpDS(8, 4, bilinear=False).eval()(torch.zeros(1, 4, 4, 4), torch.zeros(1, 4, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"), torch.no_grad():      # the ConvTranspose2d branch too
+        S.UpDS(8, 4, bilinear=False).eval()(torch.zeros(1, 8, 4, 4), torch.zeros(1, 4, 8, 8))
 
 
 def test_product_package_never_imports_oracle():
