@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
   uint64_t* a_empty = a_full + AS;                // [AS] MMAs reading the A stage retired (commit)
   uint64_t* b_full = a_empty + AS;                // [BS]
   uint64_t* b_empty = b_full + BS;                // [BS]
-  uint64_t* tmem_full = b_empty + BS;             // [2]  per pair buffer: all MMAs of the pair retired
-  uint64_t* tmem_empty = tmem_full + 2;           // [2][2] per (pair buffer, half): drained by the epilogue (128 arrivals)
+  uint64_t* tmem_full = b_empty + BS;             // [2][2] per (pair buffer, half): its MMAs retired (the epilogue starts on half 0 while half 1 finishes)
+  uint64_t* tmem_empty = tmem_full + 4;           // [2][2] per (pair buffer, half): drained by the epilogue (128 arrivals)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 4);
   float* aff = reinterpret_cast<float*>(smem + L::OFF_BAR + L::BAR_BYTES);
 
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) mbar_init(&tmem_full[s], 1);
+    for (int s = 0; s < 4; ++s) mbar_init(&tmem_full[s], 1);
     for (int s = 0; s < 4; ++s) mbar_init(&tmem_empty[s], 128);
     fence_barrier_init();
   }
@@ -347,10 +347,10 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
             } else {
               for (int kk = 0; kk < nk; ++kk) kstep(kk);
             }
+            if (i == nch - 1) umma_commit(&tmem_full[pb * 2 + h]);      // a commit tracks all MMAs issued so far by this thread
             if (h == 1) {
-              umma_commit(&a_empty[sa]);    // a commit tracks all MMAs issued so far by this thread
+              umma_commit(&a_empty[sa]);
               umma_commit(&b_empty[sb]);
-              if (i == nch - 1) umma_commit(&tmem_full[pb]);
             }
           }
           __syncwarp();
@@ -373,13 +373,14 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
       const int n0 = (pair % p.npass) * N_TILE;       // first output channel of this pass
       const uint32_t pb = (L::ACC_PAIRS == 2) ? (uint32_t)(j & 1) : 0u;
       const uint32_t use = (L::ACC_PAIRS == 2) ? (uint32_t)(j >> 1) : (uint32_t)j;
-      DT_T(te0);
-      mbar_wait(&tmem_full[pb], use & 1u);
-      DT_T(te1);
-      if (warp == 4) { DT_ADD(9, te0, te1); DT_INC(11); }
-      tc_fence_after();
+      if (warp == 4) DT_INC(11);
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
+        DT_T(te0);
+        mbar_wait(&tmem_full[pb * 2 + h], use & 1u);
+        DT_T(te1);
+        if (warp == 4) DT_ADD(9, te0, te1);
+        tc_fence_after();
         const int gy = y0 + RQ * q + 2 * cy + h, gx = x0 + 4 * cx + r;
         const bool pvalid = (gy < p.H) && (gx < p.W);
         float* ypix = p.y + (int64_t)b * p.y_bstride + (int64_t)gy * p.W + gx;
@@ -390,50 +391,47 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
           if (n0 + c0 >= p.Cout) break;
           uint32_t v[32];
           tmem_ld32(tacc + (uint32_t)c0, v);
-          float scv[32], shv[32];      // the affine of these 32 channels: broadcast LDS.128 while the TMEM load is in flight
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 a = *reinterpret_cast<const float4*>(aff + n0 + c0 + 4 * j4);
-            const float4 t = *reinterpret_cast<const float4*>(aff + L::AFF_N + n0 + c0 + 4 * j4);
-            scv[4 * j4] = a.x; scv[4 * j4 + 1] = a.y; scv[4 * j4 + 2] = a.z; scv[4 * j4 + 3] = a.w;
-            shv[4 * j4] = t.x; shv[4 * j4 + 1] = t.y; shv[4 * j4 + 2] = t.z; shv[4 * j4 + 3] = t.w;
-          }
           tmem_ld_wait();
           const int nchn = min(32, p.Cout - (n0 + c0));      // warp-uniform
           float* yp = ypix + (int64_t)(n0 + c0) * P;
+          const float* sc_p = aff + n0 + c0;                  // the affine of these 32 channels: broadcast LDS.128, 4 channels at a time
+          const float* sh_p = aff + L::AFF_N + n0 + c0;
           if (p.oc_y) {
             // channels past Cout: zero accumulators, identity affine, zero OutConv weight -> no mask needed
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 a = *reinterpret_cast<const float4*>(sc_p + 4 * j4), t = *reinterpret_cast<const float4*>(sh_p + 4 * j4);
               const float4 w4 = *reinterpret_cast<const float4*>(aff + 2 * L::AFF_N + n0 + c0 + 4 * j4);
-              const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = 4 * j4 + e;
-                oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[j]), scv[j], shv[j]), act_lo), wv[e], oc_dot);
-              }
+              oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), a.x, t.x), act_lo), w4.x, oc_dot);
+              oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), a.y, t.y), act_lo), w4.y, oc_dot);
+              oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), a.z, t.z), act_lo), w4.z, oc_dot);
+              oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), a.w, t.w), act_lo), w4.w, oc_dot);
             }
           } else if (nchn == 32) {
             // hot path: FFMA, FMNMX, pointer bump, STG per channel; each store instruction of the warp = 128 (2 x 64) contiguous bytes
             if (pvalid) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                *yp = fmaxf(fmaf(__uint_as_float(v[j]), scv[j], shv[j]), act_lo);
-                yp += P;
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 a = *reinterpret_cast<const float4*>(sc_p + 4 * j4), t = *reinterpret_cast<const float4*>(sh_p + 4 * j4);
+                yp[0] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), a.x, t.x), act_lo);
+                yp[P] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), a.y, t.y), act_lo);
+                yp[2 * P] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), a.z, t.z), act_lo);
+                yp[3 * P] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), a.w, t.w), act_lo);
+                yp += 4 * P;
               }
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (pvalid && j < nchn) yp[(int64_t)j * P] = fmaxf(fmaf(__uint_as_float(v[j]), scv[j], shv[j]), act_lo);
+              if (pvalid && j < nchn) yp[(int64_t)j * P] = fmaxf(fmaf(__uint_as_float(v[j]), sc_p[j], sh_p[j]), act_lo);
           }
         }
         if (p.oc_y && pvalid) p.oc_y[(int64_t)b * P + (int64_t)gy * p.W + gx] = oc_dot + (p.oc_b ? __ldg(p.oc_b) : 0.f);
         tc_fence_before();
         mbar_arrive(&tmem_empty[pb * 2 + h]);
+        DT_T(te2);
+        if (warp == 4) DT_ADD(10, te1, te2);
       }
-      DT_T(te2);
-      if (warp == 4) DT_ADD(10, te1, te2);
     }
   } else {
     // ===== depthwise producers: 2 groups of 4 warps; group g takes units u with u % 2 == g =====
