@@ -287,7 +287,7 @@ int smaat_pixel_shuffle2_pad_bwd(const float* g, int64_t g_bstride, float* dt, i
  * incremented by the call), so a CUDA graph holding this call follows learning-rate changes.  torch's arithmetic:
  *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr / (1-b1^t) * m / (sqrt(v) / sqrt(1-b2^t) + eps). */
 int smaat_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr,
-                    float* step, float beta1, float beta2, float eps, void* stream);
+                    float* step, double beta1, double beta2, double eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,7 +67,7 @@ SIGNATURES = {
     "smaat_convt2x2_unpack_wgrad": [_p, _p, _p, _p, _i, _i, _p],
     "smaat_pixel_shuffle2_pad_fwd": [_p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
     "smaat_pixel_shuffle2_pad_bwd": [_p, _l, _p, _i, _i, _i, _i, _i, _i, _p],
-    "smaat_adam_step": [_p, _p, _p, _p, _l, _p, _p, _f, _f, _f, _p],
+    "smaat_adam_step": [_p, _p, _p, _p, _l, _p, _p, C.c_double, C.c_double, C.c_double, _p],
 }
 _SPECIAL = {
     "smaat_abi_version": ([], _i),

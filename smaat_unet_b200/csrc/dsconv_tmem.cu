@@ -58,6 +58,7 @@ struct DtParams {
   float* oc_y;
   int C0, C1, H, W, Cout, relu, K;
   int px_tiles, py_tiles, total_pairs, nchunks;
+  int flags;           // tuning experiments (SMAAT_DT_FLAGS): bit 0 = no L2 prefetch of the next pair's boxes
   int npass;           // output-channel passes of N_TILE channels each (Cout > 128: the depthwise work is repeated per pass)
   int timing;
 };
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(&in_full[s])), "r"(x0 - 4), "r"(y0 - 1), "r"(cc), "r"(b)
               : "memory");
           // the same chunk of this CTA's NEXT pair goes to L2 now, so its TMA load later pays L2 latency only
-          if (has_next)
+          if (has_next && !(p.flags & 1))
             asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
                          "r"(nx0 - 4), "r"(ny0 - 1), "r"(cc), "r"(nb)
                          : "memory");
@@ -639,6 +640,8 @@ int dsconv_tmem_run(const float* x0, int C0, int64_t x0_bstride, const float* x1
   p.px_tiles = p.py_tiles = p.total_pairs = p.nchunks = p.npass = 0;
   static const int timing_on = [] { const char* e = getenv("SMAAT_DSCONV_TIMING"); return e ? atoi(e) : 0; }();
   p.timing = timing_on;
+  static const int flags_on = [] { const char* e = getenv("SMAAT_DT_FLAGS"); return e ? atoi(e) : 0; }();
+  p.flags = flags_on;
 
 #define DT_DISPATCH(NT, PWv)                                                  \
   return x3 ? launch_dt<NT, PWv, true>(m0, m1, mw, mwl, p, B, st)            \

@@ -15,13 +15,13 @@ namespace smaat {
 
 __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, int64_t n4, const float* __restrict__ lr_ptr,
-                                                        const float* __restrict__ step_ptr, float b1, float b2, float eps) {
+                                                        const float* __restrict__ step_ptr, double b1d, double b2d, float omb1, float omb2,
+                                                        float eps) {
+  const float b1 = (float)b1d, b2 = (float)b2d;
   const double t = (double)__ldg(step_ptr) + 1.0;             // this step's number (the counter holds completed steps)
-  const float bc1 = (float)(1.0 - pow((double)b1, t));
-  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+  const float bc1 = (float)(1.0 - pow(b1d, t));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow(b2d, t));
   const float step_size = __ldg(lr_ptr) / bc1;
-  const float omb1 = 1.f - b1, omb2 = 1.f - b2;
-  (void)b1;
   float4* p4 = reinterpret_cast<float4*>(p);
   const float4* g4 = reinterpret_cast<const float4*>(g);
   float4* m4 = reinterpret_cast<float4*>(m);
@@ -51,14 +51,16 @@ using namespace smaat;
 /* One Adam step over flat buffers of n floats (n % 4 == 0, 16-byte aligned; padding elements must hold zero gradients).
  * lr, step: device scalars (fp32; step = number of completed steps, incremented here). */
 extern "C" int smaat_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr,
-                               float* step, float beta1, float beta2, float eps, void* stream) {
+                               float* step, double beta1, double beta2, double eps, void* stream) {
   SMAAT_REQUIRE(params && grads && exp_avg && exp_avg_sq && lr && step, "adam_step: null pointer");
   SMAAT_REQUIRE(n > 0 && n % 4 == 0, "adam_step: n must be a positive multiple of 4 (pad the bucket)");
   SMAAT_REQUIRE(aligned16(params) && aligned16(grads) && aligned16(exp_avg) && aligned16(exp_avg_sq), "adam_step: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n4 = n / 4;
   const int grid = (int)(ceil_div64(n4, 256) < (int64_t)num_sms() * 8 ? ceil_div64(n4, 256) : (int64_t)num_sms() * 8);
-  adam_flat_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n4, lr, step, beta1, beta2, eps);
+  // torch evaluates 1 - beta in double and rounds once: (float)(1 - 0.999) != 1.f - 0.999f
+  adam_flat_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n4, lr, step, beta1, beta2, (float)(1.0 - beta1),
+                                         (float)(1.0 - beta2), (float)eps);
   SMAAT_LAUNCH_CHECK("smaat_adam_step");
   adam_advance_kernel<<<1, 1, 0, st>>>(step);
   SMAAT_LAUNCH_CHECK("smaat_adam_step(advance)");
