@@ -266,41 +266,57 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
     }
   } else if (warp == 3) {
     // ===== depthwise-weight stager: [channel][kk][9] weights + [kk] biases -> 20-float rows (LDS.128-able) =====
+    // One warp, one unit ahead: the global loads of unit u + 1 are issued before unit u's values are written, so their
+    // latency (an L2 round trip) overlaps a whole unit period.  [Measured: with the loads issued and consumed inside the same
+    // iteration this warp needed ~2500 cycles per unit and set the pace of the entire kernel.]
     const int Cin = p.C0 + p.C1;
-    uint32_t u = 0;
-    for (int j = 0; j < my_pairs; ++j)
-      for (int i = 0; i < nch; ++i, ++u) {
-        const int s = u % IS;
-        DT_T(ts0);
-        float v[(CC * L::WD_FLOATS + 31) / 32];
+    constexpr int NV = (CC * L::WD_FLOATS + 31) / 32;
+    // the (channel, slot) of this lane's NV elements never changes: source offsets relative to the chunk's first channel
+    int woff[NV], cl_of[NV];
 #pragma unroll
-        for (int r = 0; r < (CC * L::WD_FLOATS + 31) / 32; ++r) {      // loads first: their latency hides behind the wait
-          const int idx = r * 32 + lane;
-          const int cl = idx / L::WD_FLOATS, f = idx - cl * L::WD_FLOATS;
-          const int gch = i * CC + cl;
-          float x = 0.f;
-          if (idx < CC * L::WD_FLOATS && gch < Cin) {     // row layout: (w[2 gch][tap], w[2 gch + 1][tap]) x 9 taps, then the 2 biases
-            if (f < 18) x = __ldg(p.dw_w + (int64_t)gch * 18 + (f & 1) * 9 + (f >> 1));
-            else if (p.dw_b) x = __ldg(p.dw_b + gch * 2 + (f - 18));
-          }
-          v[r] = x;
-        }
-        DT_T(ts1);
-        mbar_wait(&in_empty[s], ((u / IS) & 1u) ^ 1u);
-        DT_T(ts2);
-        float* wd = reinterpret_cast<float*>(smem + L::OFF_WD + s * L::WD_BYTES);
+    for (int r = 0; r < NV; ++r) {
+      const int idx = r * 32 + lane;
+      const int cl = idx / L::WD_FLOATS, f = idx - cl * L::WD_FLOATS;
+      cl_of[r] = (idx < CC * L::WD_FLOATS) ? cl : -1;
+      // row layout: (w[2 ch][tap], w[2 ch + 1][tap]) x 9 taps, then the 2 biases; bias slots are flagged by a negative offset
+      woff[r] = (f < 18) ? (cl * 18 + (f & 1) * 9 + (f >> 1)) : -(cl * 2 + (f - 18)) - 1;
+    }
+    auto fetch = [&](int chunk, float (&v)[NV]) {
 #pragma unroll
-        for (int r = 0; r < (CC * L::WD_FLOATS + 31) / 32; ++r) {
-          const int idx = r * 32 + lane;
-          if (idx < CC * L::WD_FLOATS) wd[idx] = v[r];
+      for (int r = 0; r < NV; ++r) {
+        float x = 0.f;
+        if (cl_of[r] >= 0 && chunk * CC + cl_of[r] < Cin) {
+          if (woff[r] >= 0) x = __ldg(p.dw_w + (int64_t)chunk * CC * 18 + woff[r]);
+          else if (p.dw_b) x = __ldg(p.dw_b + chunk * CC * 2 + (-woff[r] - 1));
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&in_full[s]);
-        DT_T(ts3);
-        DT_ADD(15, ts1, ts2);
-        DT_ADD(16, ts0, ts3);
-        DT_INC(17);
+        v[r] = x;
       }
+    };
+    const uint32_t total_units = (uint32_t)my_pairs * (uint32_t)nch;
+    float cur[NV], nxt[NV];
+    if (total_units > 0) fetch(0, cur);
+    int chunk_next = (nch > 1) ? 1 : 0;
+    for (uint32_t u = 0; u < total_units; ++u) {
+      const int s = u % IS;
+      DT_T(ts0);
+      if (u + 1 < total_units) fetch(chunk_next, nxt);          // unit u + 1 = the next chunk (same sequence for every pair)
+      chunk_next = (chunk_next + 1 == nch) ? 0 : chunk_next + 1;
+      DT_T(ts1);
+      mbar_wait(&in_empty[s], ((u / IS) & 1u) ^ 1u);
+      DT_T(ts2);
+      float* wd = reinterpret_cast<float*>(smem + L::OFF_WD + s * L::WD_BYTES);
+#pragma unroll
+      for (int r = 0; r < NV; ++r)
+        if (cl_of[r] >= 0) wd[r * 32 + lane] = cur[r];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&in_full[s]);
+#pragma unroll
+      for (int r = 0; r < NV; ++r) cur[r] = nxt[r];
+      DT_T(ts3);
+      DT_ADD(15, ts1, ts2);
+      DT_ADD(16, ts0, ts3);
+      DT_INC(17);
+    }
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
     constexpr uint32_t idesc = make_idesc_tf32_ts(N_TILE);
