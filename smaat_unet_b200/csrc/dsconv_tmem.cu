@@ -30,7 +30,7 @@
 //   0        TMA: input halo boxes (PW + 8) x (PHP + 3) x 16 channels, OOB zero fill = padding 1; virtual concat [x0, x1]
 //   1        MMA issuer (one elected lane): per unit 2 halves x 4 k-steps x {A_hi B_hi, A_hi B_lo, A_lo B_hi}; TMEM alloc
 //   2        pointwise-weight ring loader (TMA, K-major SW128, hi | lo)
-//   3        depthwise-weight stager: the chunk's 16 x (9 taps x 2 outputs, interleaved, + 2 biases) -> shared-memory stage
+//   3        (idle; the layer's depthwise weights are staged once, by all threads, before the roles split)
 //   4..7     epilogue: tcgen05.ld (lane = pixel, 32 columns per step) -> BN affine + ReLU -> NCHW stores (or OutConv dot)
 //   8..15    two depthwise producer groups (group g takes every second unit)
 #include <stdlib.h>
@@ -106,8 +106,9 @@ struct DtCfg {
   static_assert(CHS % 32 == 8 || CHS % 32 == 24, "the 4 channel phases of a warp must fall on disjoint bank octets");
   static constexpr int IN_BYTES = CC * CHS * 4;
   static_assert(IN_BYTES % 128 == 0, "TMA destination alignment");
-  static constexpr int WD_FLOATS = 20;                    // per input channel: 2 x 9 weights + 2 biases (16-byte aligned rows)
-  static constexpr int WD_BYTES = CC * WD_FLOATS * 4;
+  static constexpr int WD_FLOATS = 20;                    // per input channel: 9 taps x (output 0, output 1) + 2 biases (16-byte aligned rows)
+  static constexpr int WD_MAXC = 512;                     // the whole layer's depthwise weights stay resident in shared memory
+  static constexpr int WD_BYTES = WD_MAXC * WD_FLOATS * 4;
   static constexpr int B_BYTES = N_TILE * TC_BK * 4;
   static constexpr int BST_BYTES = (X3 ? 2 : 1) * B_BYTES;
   static constexpr int NG = 2;                            // producer groups (128 threads each)
@@ -119,11 +120,11 @@ struct DtCfg {
   static constexpr int AS = ((512 - ACC_COLS) / AST_COLS) > 4 ? 4 : ((512 - ACC_COLS) / AST_COLS);
   static_assert(AS >= 2, "A ring");
   static constexpr int BS = (N_TILE <= 64) ? 3 : 2;
-  static constexpr int IS_FIT = (214 * 1024 - BS * BST_BYTES) / (IN_BYTES + WD_BYTES);
+  static constexpr int IS_FIT = (214 * 1024 - BS * BST_BYTES - WD_BYTES) / IN_BYTES;
   static constexpr int IS = IS_FIT > 6 ? 6 : IS_FIT;
   static_assert(IS >= 2, "input ring");
   static constexpr int OFF_WD = IS * IN_BYTES;
-  static constexpr int OFF_BR = ((OFF_WD + IS * WD_BYTES + 1023) / 1024) * 1024;
+  static constexpr int OFF_BR = ((OFF_WD + WD_BYTES + 1023) / 1024) * 1024;
   static constexpr int OFF_BAR = OFF_BR + BS * BST_BYTES;
   static constexpr int BAR_BYTES = 512;
   static constexpr int AFF_N = 512;                        // epilogue affine of ALL output channels (up to 4 passes of 128)
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* b_base = smem + L::OFF_BR;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* in_full = bars;                       // [IS] input box landed (TMA tx) + depthwise weights staged: 2 arrivals
+  uint64_t* in_full = bars;                       // [IS] input box landed (TMA tx)
   uint64_t* in_empty = in_full + IS;              // [IS] producer group done with the stage (128 arrivals)
   uint64_t* a_full = in_empty + IS;               // [AS] A operand of both halves in TMEM (128 arrivals)
   uint64_t* a_empty = a_full + AS;                // [AS] MMAs reading the A stage retired (commit)
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
     tma_prefetch_desc(&map_w);
     if (X3) tma_prefetch_desc(&map_wlo);
     for (int s = 0; s < IS; ++s) {
-      mbar_init(&in_full[s], 2);
+      mbar_init(&in_full[s], 1);
       mbar_init(&in_empty[s], 128);
     }
     for (int s = 0; s < AS; ++s) {
@@ -187,6 +188,23 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
     aff[c] = (c < p.Cout && p.scale) ? __ldg(p.scale + c) : 1.f;
     aff[L::AFF_N + c] = (c < p.Cout && p.shift) ? __ldg(p.shift + c) : 0.f;
     aff[2 * L::AFF_N + c] = (c < p.Cout && p.oc_w) ? __ldg(p.oc_w + c) : 0.f;
+  }
+  {
+    // the layer's depthwise weights, once: row c = (w[2c][tap], w[2c + 1][tap]) x 9 taps, then the 2 biases (LDS.128-able,
+    // already paired for FFMA2); channels past Cin (the last chunk's tail) are zero rows.  [A per-unit staging warp was the
+    // first design: its global-load latency, ~2500 cycles per unit, set the pace of the whole kernel.]
+    float* wd_all = reinterpret_cast<float*>(smem + L::OFF_WD);
+    const int Cin = p.C0 + p.C1;
+    const int rows = nch * CC;
+    for (int idx = threadIdx.x; idx < rows * L::WD_FLOATS; idx += blockDim.x) {
+      const int c = idx / L::WD_FLOATS, f = idx - c * L::WD_FLOATS;
+      float x = 0.f;
+      if (c < Cin) {
+        if (f < 18) x = __ldg(p.dw_w + (int64_t)c * 18 + (f & 1) * 9 + (f >> 1));
+        else if (p.dw_b) x = __ldg(p.dw_b + c * 2 + (f - 18));
+      }
+      wd_all[idx] = x;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -263,59 +281,6 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
           if (X3) tma_load_2d(b_base + sb * L::BST_BYTES + L::B_BYTES, &map_wlo, &b_full[sb], i * TC_BK, n0);
         }
       }
-    }
-  } else if (warp == 3) {
-    // ===== depthwise-weight stager: [channel][kk][9] weights + [kk] biases -> 20-float rows (LDS.128-able) =====
-    // One warp, one unit ahead: the global loads of unit u + 1 are issued before unit u's values are written, so their
-    // latency (an L2 round trip) overlaps a whole unit period.  [Measured: with the loads issued and consumed inside the same
-    // iteration this warp needed ~2500 cycles per unit and set the pace of the entire kernel.]
-    const int Cin = p.C0 + p.C1;
-    constexpr int NV = (CC * L::WD_FLOATS + 31) / 32;
-    // the (channel, slot) of this lane's NV elements never changes: source offsets relative to the chunk's first channel
-    int woff[NV], cl_of[NV];
-#pragma unroll
-    for (int r = 0; r < NV; ++r) {
-      const int idx = r * 32 + lane;
-      const int cl = idx / L::WD_FLOATS, f = idx - cl * L::WD_FLOATS;
-      cl_of[r] = (idx < CC * L::WD_FLOATS) ? cl : -1;
-      // row layout: (w[2 ch][tap], w[2 ch + 1][tap]) x 9 taps, then the 2 biases; bias slots are flagged by a negative offset
-      woff[r] = (f < 18) ? (cl * 18 + (f & 1) * 9 + (f >> 1)) : -(cl * 2 + (f - 18)) - 1;
-    }
-    auto fetch = [&](int chunk, float (&v)[NV]) {
-#pragma unroll
-      for (int r = 0; r < NV; ++r) {
-        float x = 0.f;
-        if (cl_of[r] >= 0 && chunk * CC + cl_of[r] < Cin) {
-          if (woff[r] >= 0) x = __ldg(p.dw_w + (int64_t)chunk * CC * 18 + woff[r]);
-          else if (p.dw_b) x = __ldg(p.dw_b + chunk * CC * 2 + (-woff[r] - 1));
-        }
-        v[r] = x;
-      }
-    };
-    const uint32_t total_units = (uint32_t)my_pairs * (uint32_t)nch;
-    float cur[NV], nxt[NV];
-    if (total_units > 0) fetch(0, cur);
-    int chunk_next = (nch > 1) ? 1 : 0;
-    for (uint32_t u = 0; u < total_units; ++u) {
-      const int s = u % IS;
-      DT_T(ts0);
-      if (u + 1 < total_units) fetch(chunk_next, nxt);          // unit u + 1 = the next chunk (same sequence for every pair)
-      chunk_next = (chunk_next + 1 == nch) ? 0 : chunk_next + 1;
-      DT_T(ts1);
-      mbar_wait(&in_empty[s], ((u / IS) & 1u) ^ 1u);
-      DT_T(ts2);
-      float* wd = reinterpret_cast<float*>(smem + L::OFF_WD + s * L::WD_BYTES);
-#pragma unroll
-      for (int r = 0; r < NV; ++r)
-        if (cl_of[r] >= 0) wd[r * 32 + lane] = cur[r];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&in_full[s]);
-#pragma unroll
-      for (int r = 0; r < NV; ++r) cur[r] = nxt[r];
-      DT_T(ts3);
-      DT_ADD(15, ts1, ts2);
-      DT_ADD(16, ts0, ts3);
-      DT_INC(17);
     }
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
@@ -477,7 +442,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
         mbar_wait(&in_full[s], (u / IS) & 1u);
         DT_T(tp1);
         const float* in_stage = reinterpret_cast<const float*>(smem + s * L::IN_BYTES);
-        const float* wd = reinterpret_cast<const float*>(smem + L::OFF_WD + s * L::WD_BYTES);
+        const float* wd = reinterpret_cast<const float*>(smem + L::OFF_WD) + (size_t)i * CC * L::WD_FLOATS;
         uint64_t acc[4][2][4];       // [channel i4][half / output row h][pixel] = (depthwise output 2 ci, 2 ci + 1)
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
@@ -606,6 +571,7 @@ bool dsconv_tmem_eligible(const float* x0, int C0, int64_t bs0, const float* x1,
   if (Cout < 8 || Cout > 512 || (Cout > 128 && Cout % 128 != 0)) return false;   // > 128: whole passes of 128 channels
   if (W % 4 != 0 || !aligned16(x0) || bs0 % 4 != 0) return false;
   if (C1 > 0 && (!aligned16(x1) || bs1 % 4 != 0 || C0 % 16 != 0)) return false;
+  if (((C0 + C1 + 15) / 16) * 16 > 512) return false;     // the depthwise weights of all channels stay resident in shared memory
   const int K = k * (C0 + C1);
   if (K % 4 != 0 || !aligned16(pw_w) || (pw_w_lo && !aligned16(pw_w_lo))) return false;
   return pick_pw_pair(H, W) != 0;
