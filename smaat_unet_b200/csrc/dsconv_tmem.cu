@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp >= 4 && warp < 8) {
     // ===== epilogue warps 4..7: TMEM lane quarter q = warp % 4 =====
     const int q = warp & 3;
     const int r = lane >> 3, c = lane & 7;          // TMEM lane 8r + c of the quarter <-> pixel x = 4 cx + r of row RQ q + 2 cy + h
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
         if (warp == 4) DT_ADD(10, te1, te2);
       }
     }
-  } else {
+  } else if (warp >= 8) {
     // ===== depthwise producers: 2 groups of 4 warps; group g takes units u with u % 2 == g =====
     // Thread (c = lane / 4, ph = lane % 4) of the warp with TMEM quarter q owns, in BOTH half tiles h = 0, 1, the four
     // consecutive pixels x = 4 cx .. 4 cx + 3 of row RQ q + 2 cy + h (cx = c % NX, cy = c / NX): TMEM lane 8r + c <-> pixel

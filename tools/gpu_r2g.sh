@@ -2,7 +2,9 @@
 # stager fix: parity of the fused kernel, stage timers, per-layer A/B, default bench
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu -p no:cacheprovider -k "dsconv" 2>&1 | tail -2
+timeout 200 python -m pytest tests/test_gpu_kernels.py -q -m gpu -p no:cacheprovider -k "dsconv" -x > gpurun_out/pytest_r2g.log 2>&1; rc=$?
+tail -2 gpurun_out/pytest_r2g.log
+if [ $rc -ne 0 ]; then echo "parity failed or hung (rc=$rc): stopping"; grep -E "^(FAILED|E  )" gpurun_out/pytest_r2g.log | head -5; exit 1; fi
 for a in "12 288 64" "64 288 64" "128 288 64" "64 144 128" "256 144 128" "256 72 256"; do timeout 120 python tools/dt_timing.py $a tf32x3 2>&1 | tail -5; done
 echo "== tmem kernel"; timeout 120 python tools/time_ds.py tf32x3 tmem 2>&1 | tail -14
 echo "== tmem kernel, tf32"; timeout 120 python tools/time_ds.py tf32 tmem 2>&1 | tail -14
