@@ -93,7 +93,7 @@ __device__ __forceinline__ uint64_t fma2_bcast(uint64_t a, float b, uint64_t c) 
 __device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int N_TILE, int PW, bool X3>
+template <int N_TILE, int PW, bool X3, bool BIG>
 struct DtCfg {
   static constexpr int KPL = 2;
   static constexpr int CC = TC_BK / KPL;                 // 16 input channels per chunk
@@ -107,8 +107,8 @@ struct DtCfg {
   static constexpr int IN_BYTES = CC * CHS * 4;
   static_assert(IN_BYTES % 128 == 0, "TMA destination alignment");
   static constexpr int WD_FLOATS = 20;                    // per input channel: 9 taps x (output 0, output 1) + 2 biases (16-byte aligned rows)
-  static constexpr int WD_MAXC = 512;                     // the whole layer's depthwise weights stay resident in shared memory
-  static constexpr int WD_BYTES = WD_MAXC * WD_FLOATS * 4;
+  static constexpr int WD_MAXC = BIG ? 512 : 256;         // the whole layer's depthwise weights stay resident in shared memory:
+  static constexpr int WD_MAX_BYTES = WD_MAXC * WD_FLOATS * 4;   // nchunks * 16 rows of 80 B at the END of the carve-up (run-time size)
   static constexpr int B_BYTES = N_TILE * TC_BK * 4;
   static constexpr int BST_BYTES = (X3 ? 2 : 1) * B_BYTES;
   static constexpr int NG = 2;                            // producer groups (128 threads each)
@@ -119,26 +119,26 @@ struct DtCfg {
   static constexpr int AST_COLS = 2 * AH_COLS;
   static constexpr int AS = ((512 - ACC_COLS) / AST_COLS) > 4 ? 4 : ((512 - ACC_COLS) / AST_COLS);
   static_assert(AS >= 2, "A ring");
-  static constexpr int BS = (N_TILE <= 64) ? 3 : 2;
-  static constexpr int IS_FIT = (214 * 1024 - BS * BST_BYTES - WD_BYTES) / IN_BYTES;
-  static constexpr int IS = IS_FIT > 6 ? 6 : IS_FIT;
+  // BIG (more than 256 input channels: 40 KB of depthwise weights, >= 16 chunks per pair) trades ring depth for the table
+  static constexpr int BS = BIG ? 2 : 3;                  // pointwise-weight ring: its TMA loads must cover an L2 round trip
+  static constexpr int IS = (N_TILE <= 64 && !BIG) ? 5 : 3;   // input ring (the TMA thread runs far ahead of the producers anyway)
   static_assert(IS >= 2, "input ring");
-  static constexpr int OFF_WD = IS * IN_BYTES;
-  static constexpr int OFF_BR = ((OFF_WD + WD_BYTES + 1023) / 1024) * 1024;
+  static constexpr int OFF_BR = ((IS * IN_BYTES + 1023) / 1024) * 1024;
   static constexpr int OFF_BAR = OFF_BR + BS * BST_BYTES;
   static constexpr int BAR_BYTES = 512;
   static constexpr int AFF_N = 512;                        // epilogue affine of ALL output channels (up to 4 passes of 128)
-  static constexpr int TOTAL = OFF_BAR + BAR_BYTES + 3 * AFF_N * 4 + 1024;
-  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+  static constexpr int OFF_WD = OFF_BAR + BAR_BYTES + 3 * AFF_N * 4;
+  static constexpr int FIXED = OFF_WD + 1024;             // + alignment slack; + the depthwise-weight table = dynamic shared memory
+  static_assert(FIXED + WD_MAX_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(N_TILE <= AFF_N, "epilogue affine staging");
   static constexpr int THREADS = 128 + 128 + 128 * NG;
 };
 
-template <int N_TILE, int PW, bool X3>
-__global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
+template <int N_TILE, int PW, bool X3, bool BIG>
+__global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
     dsconv_tmem_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constant__ CUtensorMap map_in1,
                        const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo, const DtParams p) {
-  using L = DtCfg<N_TILE, PW, X3>;
+  using L = DtCfg<N_TILE, PW, X3, BIG>;
   constexpr int IS = L::IS, AS = L::AS, BS = L::BS, CC = L::CC, BW = L::BW, CHS = L::CHS, NX = L::NX, RQ = L::RQ, PHP = L::PHP;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -526,15 +526,15 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3>::THREADS, 1)
   }
 }
 
-template <int N_TILE, int PW, bool X3>
+template <int N_TILE, int PW, bool X3, bool BIG>
 static int launch_dt(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mw, const CUtensorMap& mwl, DtParams p, int B,
                      cudaStream_t st) {
-  using L = DtCfg<N_TILE, PW, X3>;
-  auto kern = dsconv_tmem_kernel<N_TILE, PW, X3>;
+  using L = DtCfg<N_TILE, PW, X3, BIG>;
+  auto kern = dsconv_tmem_kernel<N_TILE, PW, X3, BIG>;
   static std::atomic<uint64_t> attr_mask{0};   // cudaFuncSetAttribute is per device
   if (first_use_on_device(attr_mask)) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-    if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "dsconv(tmem): smem attribute (%d B): %s", L::TOTAL, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::FIXED + L::WD_MAX_BYTES);
+    if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "dsconv(tmem): smem attribute (%d B): %s", L::FIXED + L::WD_MAX_BYTES, cudaGetErrorString(e));
   }
   p.px_tiles = ceil_div(p.W, PW);
   p.py_tiles = ceil_div(p.H, L::PHP);
@@ -544,7 +544,7 @@ static int launch_dt(const CUtensorMap& m0, const CUtensorMap& m1, const CUtenso
   p.total_pairs = (int)total;
   p.nchunks = ceil_div(p.C0 + p.C1, L::CC);
   const int grid = p.total_pairs < num_sms() ? p.total_pairs : num_sms();
-  kern<<<grid, L::THREADS, L::TOTAL, st>>>(m0, m1, mw, mwl, p);
+  kern<<<grid, L::THREADS, L::FIXED + p.nchunks * L::CC * L::WD_FLOATS * 4, st>>>(m0, m1, mw, mwl, p);
   SMAAT_LAUNCH_CHECK("smaat_dsconv_fwd(tmem)");
   return SMAAT_OK;
 }
@@ -625,9 +625,12 @@ int dsconv_tmem_run(const float* x0, int C0, int64_t x0_bstride, const float* x1
   static const int flags_on = [] { const char* e = getenv("SMAAT_DT_FLAGS"); return e ? atoi(e) : 0; }();
   p.flags = flags_on;
 
-#define DT_DISPATCH(NT, PWv)                                                  \
-  return x3 ? launch_dt<NT, PWv, true>(m0, m1, mw, mwl, p, B, st)            \
-            : launch_dt<NT, PWv, false>(m0, m1, mw, mwl, p, B, st)
+  const bool big = ((C0 + C1 + 15) / 16) * 16 > 256;
+#define DT_DISPATCH(NT, PWv)                                                                               \
+  return x3 ? (big ? launch_dt<NT, PWv, true, true>(m0, m1, mw, mwl, p, B, st)                             \
+                   : launch_dt<NT, PWv, true, false>(m0, m1, mw, mwl, p, B, st))                           \
+            : (big ? launch_dt<NT, PWv, false, true>(m0, m1, mw, mwl, p, B, st)                            \
+                   : launch_dt<NT, PWv, false, false>(m0, m1, mw, mwl, p, B, st))
   if (n_tile == 64) {
     if (pw == 32) { DT_DISPATCH(64, 32); } else { DT_DISPATCH(64, 16); }
   } else {
