@@ -285,20 +285,27 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
     constexpr uint32_t idesc = make_idesc_tf32_ts(N_TILE);
+    // The waits for unit u + 1's operands are taken BETWEEN the two half-tile batches of unit u: a barrier test costs the
+    // issuing thread ~100-200 cycles even when the data is there, and its MMA queue is short -- taken in front of a unit's first
+    // MMA (as the first version did) they left the tensor pipe idle ~350 cycles per unit.
+    const uint32_t total_units = (uint32_t)my_pairs * (uint32_t)nch;
+    auto wait_operands = [&](uint32_t uu) {
+      DT_T(tm0);
+      mbar_wait(&a_full[uu % AS], (uu / AS) & 1u);
+      DT_T(tm1);
+      mbar_wait(&b_full[uu % BS], (uu / BS) & 1u);
+      DT_T(tm2);
+      DT_ADD(4, tm0, tm1);
+      DT_ADD(5, tm1, tm2);
+      DT_INC(8);
+    };
     uint32_t u = 0;
+    if (total_units > 0) wait_operands(0);
     for (int j = 0; j < my_pairs; ++j) {
       const uint32_t pb = (L::ACC_PAIRS == 2) ? (uint32_t)(j & 1) : 0u;
       const uint32_t use = (L::ACC_PAIRS == 2) ? (uint32_t)(j >> 1) : (uint32_t)j;    // how often this pair buffer was used before
       for (int i = 0; i < nch; ++i, ++u) {
         const int sa = u % AS, sb = u % BS;
-        DT_T(tm0);
-        mbar_wait(&a_full[sa], (u / AS) & 1u);
-        DT_T(tm1);
-        mbar_wait(&b_full[sb], (u / BS) & 1u);
-        DT_T(tm2);
-        DT_ADD(4, tm0, tm1);
-        DT_ADD(5, tm1, tm2);
-        DT_INC(8);
         const int kc = min(TC_BK, p.K - i * TC_BK);
         const int nk = (kc + 7) >> 3;
 #pragma unroll
@@ -338,6 +345,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
           __syncwarp();
           DT_T(tm5);
           DT_ADD(7, tm4, tm5);
+          if (h == 0 && u + 1 < total_units) wait_operands(u + 1);
         }
       }
     }
