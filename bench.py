@@ -33,6 +33,12 @@ METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
 B_PER_GPU, C_IN, SIZE = 32, 12, 288
 
 
+def note(msg):
+    """Progress marker on stderr (stdout carries only the JSON line)."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def peaks():
     """(HBM GB/s, dense tf32 TFLOP/s, source).  tf32 tensor peak = half the measured cuBLAS bf16 burst figure (a kernel
     timed launch by launch); nominal ratio bf16:tf32 = 2:1 (B200_PROFILING.md)."""
@@ -337,7 +343,9 @@ def main():
     model = S.SmaAt_UNet(C_IN, 1, kernels_per_layer=2)
     randomise_bn(model, gen)
     model = model.to(dev).eval()
+    note("building the inference session (warm-up + CUDA-graph capture)")
     sess = InferenceSession(model, B_PER_GPU, (C_IN, SIZE, SIZE), device=dev, use_graph=not args.no_graph)
+    note("session ready")
 
     # two resident input batches (alternated); a step touches ~40 GB of activations >> 126 MB L2
     xs = [torch.rand((B_PER_GPU, C_IN, SIZE, SIZE), generator=gen).to(dev) for _ in range(2)]
@@ -363,6 +371,7 @@ def main():
         return reduce_max(a0.elapsed_time(a1))
 
     # ---------------- device-resident throughput ("value") ----------------
+    note("timing: device-resident replays")
     sampler = ClockSampler(local)
     sampler.start()
     ms = timed_replays(sess)
@@ -389,6 +398,7 @@ def main():
         assert err <= tol, f"bench: the timed path disagrees with the oracle: {err:.3e} > {tol:.1e}"
 
     # ---------------- end to end through the public API, host buffers ----------------
+    note("timing: end to end (submit / collect)")
     for i in range(args.warmup):
         sess.submit(host[i % 2])
         sess.collect()
@@ -410,6 +420,7 @@ def main():
 
     # ---------------- the same forward through the plain reference-order calls only ----------------
     # (what a patch_reference() user of the unchanged reference classes executes: no OutConv-in-epilogue fusion)
+    note("timing: plain reference-order calls")
     sess_api = InferenceSession(model, B_PER_GPU, (C_IN, SIZE, SIZE), device=dev, use_graph=not args.no_graph, serving_fusions=False)
     api_ms = timed_replays(sess_api)
     via_api = {"value": world * B_PER_GPU * args.steps / (api_ms * 1e-3), "unit": "frames/s", "ms_per_step": api_ms / args.steps,
@@ -421,6 +432,7 @@ def main():
     # ---------------- reported-only: same measurement in the single-pass TF32 mode ----------------
     # (what the reference itself computes on a GPU: cuDNN allow_tf32=True; ~1e-3 relative error instead of 1e-6)
     alt = None
+    note("timing: tf32 mode / eager baseline / per-kernel roofline pass")
     if args.mode == "tf32x3" and not args.no_alt:
         S.set_pointwise_mode("tf32")
         sess2 = InferenceSession(model, B_PER_GPU, (C_IN, SIZE, SIZE), device=dev, use_graph=not args.no_graph)
@@ -508,6 +520,7 @@ def main():
 
     # ---------------- CPU baseline (oracle port), rank 0, N=1 only: the full B=32 batch, once ----------------
     cpu = None
+    note("cpu baseline")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = usable_cpus()
         n = B_PER_GPU
@@ -519,6 +532,7 @@ def main():
     # ---------------- training step (configs[2]; configs[3] split when N > 1): reported beside the headline ----------------
     e2e_meta = (sess.h2d_bytes_per_step, sess.d2h_bytes_per_step, sess.graph is not None)
     train = None
+    note("training leg")
     if not args.no_train:
         del sess
         S.ops.bump_weights_generation()
@@ -528,6 +542,7 @@ def main():
         except Exception as e:          # a reported-only leg must never take the headline line down
             train = {"error": repr(e)[:300]}
 
+    note("done")
     if rank == 0:
         out = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
