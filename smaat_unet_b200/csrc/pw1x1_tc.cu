@@ -447,7 +447,10 @@ int pw1x1_tc_launch(const float* x, const float* w, const float* w_lo, const flo
   SMAAT_REQUIRE(!x3 || w_lo, "pw1x1(tc): TF32X3 needs w_lo (see smaat_split_tf32)");
   SMAAT_REQUIRE(Cout <= 512 || (!scale && !shift), "pw1x1(tc): Cout=%d > 512 with an epilogue affine (smem staging holds 512 channels)", Cout);
   // the tile shape depends on the layer only, never on the batch: results stay bit-identical across batch sizes
-  const int n_tile = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
+  // ... with one exception that still depends on the layer alone: tiny planes (P <= 512, the 18 x 18 bottleneck) have only 3 pixel
+  // tiles per image; at N_TILE = 256 the B = 32 forward is 192 tiles on 148 SMs (2 rounds, 65 % filled), at 128 it is 384 tiles of
+  // half the work (3 rounds = 1.5 of the former)
+  const int n_tile = Cout > 128 ? (P <= 512 ? 128 : 256) : (Cout > 64 ? 128 : 64);
 
   CUtensorMap mx, mw, mwl;
   {

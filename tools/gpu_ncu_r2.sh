@@ -9,12 +9,12 @@ B="python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-alt --
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${T}.csv $B > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
 # the fused DS kernels of one forward in steady state (skip the warm-up forwards' launches)
-timeout 1200 ncu --set full --clock-control none -k regex:dsconv_tmem -s 36 -c 12 -o gpurun_out/prof_${T}_dsconv -f $B > gpurun_out/ncu_ds.log 2>&1
+timeout 1200 ncu --set full --clock-control none -k regex:dsconv_tmem -s 36 -c 7 -o gpurun_out/prof_${T}_dsconv -f $B > gpurun_out/ncu_ds.log 2>&1
 echo "dsconv_tmem full rc=$?"
-timeout 900 ncu --set full --clock-control none -k regex:pw1x1_tc_kernel -s 18 -c 6 -o gpurun_out/prof_${T}_pw -f $B > gpurun_out/ncu_pw.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:pw1x1_tc_kernel -s 18 -c 3 -o gpurun_out/prof_${T}_pw -f $B > gpurun_out/ncu_pw.log 2>&1
 echo "pw full rc=$?"
-timeout 900 ncu --set full --clock-control none -k "regex:cbam_|upsample2x|dw3x3_kernel" -s 48 -c 24 -o gpurun_out/prof_${T}_cbam_up_dw -f $B > gpurun_out/ncu_cbam.log 2>&1
+timeout 900 ncu --set full --clock-control none -k "regex:cbam_|upsample2x" -s 36 -c 9 -o gpurun_out/prof_${T}_cbam_up_dw -f $B > gpurun_out/ncu_cbam.log 2>&1
 echo "cbam+upsample+dw full rc=$?"
-SMAAT_FUSE_DS=0 timeout 900 ncu --set full --clock-control none -k regex:dw3x3_kernel -s 64 -c 2 -o gpurun_out/prof_${T}_dw_unfused -f $B > gpurun_out/ncu_dw.log 2>&1
+SMAAT_FUSE_DS=0 timeout 900 ncu --set full --clock-control none -k regex:dw3x3_kernel -s 64 -c 1 -o gpurun_out/prof_${T}_dw_unfused -f $B > gpurun_out/ncu_dw.log 2>&1
 echo "dw (unfused pass) full rc=$?"
 ls -la gpurun_out/prof_${T}_*.ncu-rep gpurun_out/launches_${T}.csv
