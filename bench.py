@@ -322,10 +322,18 @@ def main():
         run_reference(args, rank)
         return
 
-    if world > 1:      # leave NCCL's init lines (comm nranks, NVLS / ring choice) in the run's stderr, never in stdout
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    nccl_log = None
+    if world > 1 and "NCCL_DEBUG" not in os.environ:
+        # keep NCCL's init lines (comm nranks, rings / NVLS) as evidence -- in a FILE (never stdout: the JSON line must stay alone
+        # there), echoed to stderr by rank 0 at the end
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out", "nccl"), exist_ok=True)
+            nccl_log = os.path.join(ROOT, "gpurun_out", "nccl", f"rank{rank}.log")
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
+            os.environ["NCCL_DEBUG_FILE"] = nccl_log
+        except OSError:
+            nccl_log = None
     import torch.distributed as dist
     import smaat_unet_b200 as S
     from smaat_unet_b200 import parallel as PAR
@@ -560,6 +568,10 @@ def main():
             "alt_mode": alt, "clocks": clocks, "gpu_launches": int(launches),
         }
         print(json.dumps(out), flush=True)
+        if nccl_log and os.path.exists(nccl_log):
+            keep = [l.rstrip() for l in open(nccl_log, errors="replace") if any(k in l for k in ("nranks", "NVLS", "Connected all", "Channel 00/"))]
+            for l in keep[:12]:
+                print("[nccl] " + l[:220], file=sys.stderr)
     if world > 1:
         dist.destroy_process_group()
 

@@ -5,7 +5,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 \
   > gpurun_out/bench_n$N.log 2> gpurun_out/bench_n$N.err; echo "bench N=$N rc=$?"
-grep -E "NCCL INFO (comm|Connected|.*nranks|.*NVLS)" gpurun_out/bench_n$N.err | head -8 | cut -c1-220
+grep -E "^\[nccl\]" gpurun_out/bench_n$N.err | head -8 | cut -c1-220
 python - <<PY
 import json
 d=json.loads(open('gpurun_out/bench_n$N.log').read().strip().splitlines()[-1])
