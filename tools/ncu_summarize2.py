@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.chdir(ROOT)
 out = [f"# Round {tag} -- ncu evidence (tf32x3 mode, B=32, 12x288x288)\n",
        "Commands: tools/gpu_ncu_r2.sh (under gpurun, 1 GPU): `ncu --metrics gpu__time_duration.sum --clock-control none` launch list of",
-       "`bench.py --steps 1 --warmup 3 --no-graph`, and `ncu --set full --clock-control none --import-source on -k regex:<kernel>` captures.\n"]
+       "`bench.py --steps 1 --warmup 3 --no-graph`, and `ncu --set full --clock-control none -k regex:<kernel>` captures.\n"]
 
 
 def short(n):
