@@ -323,14 +323,14 @@ def main():
         return
 
     nccl_log = None
-    if world > 1 and "NCCL_DEBUG" not in os.environ:
+    if world > 1 and "NCCL_DEBUG_FILE" not in os.environ:
         # keep NCCL's init lines (comm nranks, rings / NVLS) as evidence -- in a FILE (never stdout: the JSON line must stay alone
         # there), echoed to stderr by rank 0 at the end
         try:
             os.makedirs(os.path.join(ROOT, "gpurun_out", "nccl"), exist_ok=True)
             nccl_log = os.path.join(ROOT, "gpurun_out", "nccl", f"rank{rank}.log")
-            os.environ["NCCL_DEBUG"] = "INFO"
-            os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
+            os.environ["NCCL_DEBUG"] = "INFO"                 # (overrides a quieter preset: the file keeps stdout / stderr clean)
+            os.environ["NCCL_DEBUG_SUBSYS"] = "INIT,ENV"
             os.environ["NCCL_DEBUG_FILE"] = nccl_log
         except OSError:
             nccl_log = None
