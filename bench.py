@@ -312,6 +312,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the reported-only tf32 measurement")
     ap.add_argument("--no-train", action="store_true", help="skip the reported-only training-step leg")
+    ap.add_argument("--leg-timeout", type=int, default=600, help="watchdog (s) over the explanatory legs after value / e2e are measured")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: W >= 3"
 
@@ -426,6 +427,42 @@ def main():
     assert abs(chk - chk_expect) <= 1e-6 * max(1.0, abs(chk_expect)), \
         f"bench: e2e results are not the results of the submitted batches (checksum {chk!r} != {chk_expect!r})"
 
+    # ---------------- everything below is explanatory; the headline (value, e2e) is in hand.  A watchdog prints the line with what
+    # has been measured so far if a later leg stalls (a reported-only leg must never cost the run its number) ----------------
+    via_api = alt = gpu_eager = roof = roof_dw = cpu = train = None
+    kernels = {}
+    e2e_meta = (sess.h2d_bytes_per_step, sess.d2h_bytes_per_step, sess.graph is not None)
+    emitted = threading.Event()
+
+    def build_out(incomplete=None):
+        out = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: full SmaAt-UNet forward (eval), batch=32 per GPU, 12->1ch 288x288, kernels_per_layer=2",
+                       "global_batch": B_PER_GPU * world, "pointwise": args.mode, "cuda_graph": e2e_meta[2],
+                       "parallelism": f"batch-sharded x{world}, no collective",
+                       "l2": "inputs alternate between 2 buffers; a step streams ~40 GB of activations (>> 126 MB L2)"},
+            "roofline": roof, "depthwise_roofline": roof_dw, "kernels": kernels, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": e2e_meta[0],
+                    "d2h_bytes_per_step": e2e_meta[1], "ms_per_step": 1e3 * e2e_s / args.steps, "checksum": chk,
+                    "checksum_expected": chk_expect},
+            "parity": parity, "via_reference_api": via_api, "gpu_eager_baseline": gpu_eager, "train": train,
+            "alt_mode": alt, "clocks": clocks, "gpu_launches": int(launches),
+        }
+        if incomplete:
+            out["incomplete"] = incomplete
+        return out
+
+    def watchdog():
+        if not emitted.wait(args.leg_timeout):
+            if rank == 0:
+                print(json.dumps(build_out(f"an explanatory leg did not finish within {args.leg_timeout} s; keys still null were not measured")),
+                      flush=True)
+            os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+
     # ---------------- the same forward through the plain reference-order calls only ----------------
     # (what a patch_reference() user of the unchanged reference classes executes: no OutConv-in-epilogue fusion)
     note("timing: plain reference-order calls")
@@ -439,7 +476,6 @@ def main():
 
     # ---------------- reported-only: same measurement in the single-pass TF32 mode ----------------
     # (what the reference itself computes on a GPU: cuDNN allow_tf32=True; ~1e-3 relative error instead of 1e-6)
-    alt = None
     note("timing: tf32 mode / eager baseline / per-kernel roofline pass")
     if args.mode == "tf32x3" and not args.no_alt:
         S.set_pointwise_mode("tf32")
@@ -451,12 +487,10 @@ def main():
         S.ops.bump_weights_generation()
 
     # ---------------- reported-only: eager PyTorch (ATen/cuDNN) on the SAME GPU -- the practical bar ----------------
-    gpu_eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         gpu_eager = eager_gpu_baseline(model, xs, dev)
 
     # ---------------- roofline: per-kernel timing, CUDA events on the launching stream ----------------
-    roof, roof_dw, kernels = None, None, {}
     if rank == 0:
         hbm, tf32_peak, src = peaks()
         fwd = model.forward_serving
@@ -527,7 +561,6 @@ def main():
                        "algorithmic_bytes_per_step": a2["bytes"] / 3, "ms_per_step": a2["ms"] / 3}
 
     # ---------------- CPU baseline (oracle port), rank 0, N=1 only: the full B=32 batch, once ----------------
-    cpu = None
     note("cpu baseline")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = usable_cpus()
@@ -538,8 +571,6 @@ def main():
                          f"(torch CPU fp32, {threads} threads)"}
 
     # ---------------- training step (configs[2]; configs[3] split when N > 1): reported beside the headline ----------------
-    e2e_meta = (sess.h2d_bytes_per_step, sess.d2h_bytes_per_step, sess.graph is not None)
-    train = None
     note("training leg")
     if not args.no_train:
         del sess
@@ -551,22 +582,9 @@ def main():
             train = {"error": repr(e)[:300]}
 
     note("done")
+    emitted.set()
     if rank == 0:
-        out = {
-            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: full SmaAt-UNet forward (eval), batch=32 per GPU, 12->1ch 288x288, kernels_per_layer=2",
-                       "global_batch": B_PER_GPU * world, "pointwise": args.mode, "cuda_graph": e2e_meta[2],
-                       "parallelism": f"batch-sharded x{world}, no collective",
-                       "l2": "inputs alternate between 2 buffers; a step streams ~40 GB of activations (>> 126 MB L2)"},
-            "roofline": roof, "depthwise_roofline": roof_dw, "kernels": kernels, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": e2e_meta[0],
-                    "d2h_bytes_per_step": e2e_meta[1], "ms_per_step": 1e3 * e2e_s / args.steps, "checksum": chk,
-                    "checksum_expected": chk_expect},
-            "parity": parity, "via_reference_api": via_api, "gpu_eager_baseline": gpu_eager, "train": train,
-            "alt_mode": alt, "clocks": clocks, "gpu_launches": int(launches),
-        }
+        out = build_out()
         print(json.dumps(out), flush=True)
         if nccl_log and os.path.exists(nccl_log):
             keep = [l.rstrip() for l in open(nccl_log, errors="replace") if any(k in l for k in ("nranks", "NVLS", "Connected all", "Channel 00/"))]
