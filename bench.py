@@ -274,7 +274,21 @@ def train_leg(args, dev, rank, world, S, PAR, per_gpu_batches):
             cfg["exposed_allreduce_ms"] = ms - ms_nc
         out["configs"].append(cfg)
         sess.close()
-        del sess, model, xs, ys
+        del sess
+        if B == per_gpu_batches[0]:
+            # memory/time trade-off (TrainSession(recompute_depthwise=True)): depthwise results recomputed in the backward
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats(dev)
+            try:
+                sess = TrainSession(model, B, (C_IN, SIZE, SIZE), lr=1e-3, device=dev, use_graph=not args.no_graph, recompute_depthwise=True)
+                ms_r = timed(k)
+                cfg["recompute_depthwise"] = {"ms_per_step": ms_r, "max_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9,
+                                              "launches_per_step": sess.launches_per_step}
+                sess.close()
+                del sess
+            except torch.OutOfMemoryError:
+                cfg["recompute_depthwise"] = {"error": "out of memory"}
+        del model, xs, ys
     torch.cuda.empty_cache()
     return out
 

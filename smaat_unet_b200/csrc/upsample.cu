@@ -94,12 +94,12 @@ __global__ void __launch_bounds__(UP_THREADS) upsample2x_pad_kernel(const float*
 }
 
 // ---- streaming variant (128-bit stores, no shared memory, no barriers) ------------------------------------------------
-// A thread owns 4 consecutive output columns and UPS_ROWS consecutive output rows of one plane.  Its 4 columns need at
+// A thread owns 4 consecutive output columns and walks UPS_ROWS consecutive output rows of one plane.  Its 4 columns need at
 // most 4 consecutive source columns (src = dst * (W-1)/(2W-1) < dst / 2 + 1): the horizontally blended source row
 // h[j] = w_x0[j] * v[x0[j]] + w_x1[j] * v[x0[j] + 1] is kept in registers for source rows y0 and y0 + 1 and recomputed only when
 // the walk crosses into the next source row (every ~2 output rows): ~2.5 scalar loads (L1 / L2 hits: the source is 4x smaller
 // than the output and every value is read by ~4 neighbouring threads), 16 flops and one 128-bit store per 4 outputs.
-constexpr int UPS_ROWS = 6;   // 5 * ry < 2.5: the rows of a thread span at most source rows yf .. yf + 3 (+ 1 neighbour)
+constexpr int UPS_ROWS = 8;
 __global__ void __launch_bounds__(256) upsample2x_pad_stream_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t y_bstride,
                                                                     int C, int H, int W, int Ho, int Wo, int pad_t, int pad_l, float ry,
                                                                     float rx, int quads, int row_groups, int64_t planes) {
@@ -126,20 +126,15 @@ __global__ void __launch_bounds__(256) upsample2x_pad_stream_kernel(const float*
     wx1[j] = in ? lx : 0.f;
   }
   const float* plane = x + ((int64_t)b * C + c) * H * W;
+  auto hrow = [&](int yy, float (&h)[4]) {
+    const float* r = plane + (int64_t)yy * W;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = wx0[j] * __ldg(r + xi[j]) + wx1[j] * __ldg(r + min(xi[j] + 1, W - 1));
+  };
   float* dst = y + (int64_t)b * y_bstride + (int64_t)c * Ho * Wo + ox;
+  float h0[4], h1[4];
+  int cur = -1;                                        // source row held in h0 (h1 = row min(cur + 1, H - 1))
   const int oy0 = rg * UPS_ROWS;
-  // The UPS_ROWS = 6 output rows of this thread read at most 5 consecutive source rows (src = dst * ry, ry < 1/2: y0 - yf <= 3, + the
-  // y0 + 1 neighbour): blend all five horizontally up front (40 loads in flight), then every output row is a two-row blend picked
-  // by a small, almost always warp-uniform, switch -- ~12 instructions per output instead of ~33 in the first streaming version,
-  // which re-derived its source rows inside the row loop and was issue-bound (70 % issue slots, 62 % of HBM).
-  const int yf = min((int)(ry * (float)max(oy0 - pad_t, 0)), H - 1);
-  float hs[5][4];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const float* r = plane + (int64_t)min(yf + k, H - 1) * W;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) hs[k][j] = wx0[j] * __ldg(r + xi[j]) + wx1[j] * __ldg(r + min(xi[j] + 1, W - 1));
-  }
 #pragma unroll
   for (int r = 0; r < UPS_ROWS; ++r) {
     const int oy = oy0 + r;
@@ -150,14 +145,18 @@ __global__ void __launch_bounds__(256) upsample2x_pad_stream_kernel(const float*
     const int y0 = min((int)sy, H - 1);
     const float ly = sy - (float)y0;
     const float w0 = in ? 1.f - ly : 0.f, w1 = in ? ly : 0.f;
-    float4 o;
-    switch (y0 - yf) {     // rows past the last source row repeat it with weight ly = 0 (torch: y1 = min(y0 + 1, H - 1))
-      case 0: o = make_float4(w0 * hs[0][0] + w1 * hs[1][0], w0 * hs[0][1] + w1 * hs[1][1], w0 * hs[0][2] + w1 * hs[1][2], w0 * hs[0][3] + w1 * hs[1][3]); break;
-      case 1: o = make_float4(w0 * hs[1][0] + w1 * hs[2][0], w0 * hs[1][1] + w1 * hs[2][1], w0 * hs[1][2] + w1 * hs[2][2], w0 * hs[1][3] + w1 * hs[2][3]); break;
-      case 2: o = make_float4(w0 * hs[2][0] + w1 * hs[3][0], w0 * hs[2][1] + w1 * hs[3][1], w0 * hs[2][2] + w1 * hs[3][2], w0 * hs[2][3] + w1 * hs[3][3]); break;
-      default: o = make_float4(w0 * hs[3][0] + w1 * hs[4][0], w0 * hs[3][1] + w1 * hs[4][1], w0 * hs[3][2] + w1 * hs[4][2], w0 * hs[3][3] + w1 * hs[4][3]); break;
+    if (y0 != cur) {
+      if (y0 == cur + 1 && cur >= 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h0[j] = h1[j];
+      } else {
+        hrow(y0, h0);
+      }
+      hrow(min(y0 + 1, H - 1), h1);
+      cur = y0;
     }
-    *reinterpret_cast<float4*>(dst + (int64_t)oy * Wo) = o;
+    *reinterpret_cast<float4*>(dst + (int64_t)oy * Wo) =
+        make_float4(w0 * h0[0] + w1 * h1[0], w0 * h0[1] + w1 * h1[1], w0 * h0[2] + w1 * h1[2], w0 * h0[3] + w1 * h1[3]);
   }
 }
 

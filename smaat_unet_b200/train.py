@@ -37,12 +37,13 @@ _ALIGN = 64          # floats: every parameter starts on a 256-byte boundary of 
 
 class TrainSession:
     def __init__(self, model, batch, in_shape, lr=1e-3, device=None, use_graph=True, metrics=None, warmup=3,
-                 betas=(0.9, 0.999), eps=1e-8, overlap_allreduce=True):
+                 betas=(0.9, 0.999), eps=1e-8, overlap_allreduce=True, recompute_depthwise=False):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.model = model.to(self.device).train()
         self.batch, self.in_shape = int(batch), tuple(in_shape)
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.use_graph = bool(use_graph)
+        self.recompute_depthwise = bool(recompute_depthwise)   # functional.set_recompute_depthwise for this session's forwards
         self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
         if self.world > 1:
             # replicas must start identical (what DDP / Lightning do at construction): rank 0's parameters AND buffers
@@ -121,7 +122,11 @@ class TrainSession:
     # ---- the pieces of a step ----------------------------------------------------------------------------
     def _forward_loss(self):
         self._bnd.clear()
-        pred = self.model(self.x)
+        old = Fn.set_recompute_depthwise(self.recompute_depthwise)
+        try:
+            pred = self.model(self.x)
+        finally:
+            Fn.set_recompute_depthwise(old)
         return step_loss(pred, self.y, self.metrics)      # loss_func + metrics.update in one pass (metrics.py)
 
     def _phase1(self):

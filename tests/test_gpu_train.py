@@ -377,3 +377,40 @@ def test_two_phase_backward_is_verified_not_assumed():
         for (k, p), q in zip(m.named_parameters(), m_ref.parameters()):
             assert (p.grad - q.grad).abs().max().item() <= 2e-3 * gmax, (n_cbams, k)
         sess.close()
+
+
+def test_recompute_depthwise_is_bit_identical_and_saves_memory():
+    """functional.set_recompute_depthwise drops the depthwise results after the forward and re-runs the same kernel in the
+    backward: gradients are bit-identical (same kernel, same inputs), peak memory of a forward+backward goes down."""
+    from smaat_unet_b200 import functional as Fn
+    torch.manual_seed(5)
+    m = S.SmaAt_UNet(12, 1, kernels_per_layer=2).cuda().train()
+    x = torch.rand(4, 12, 96, 96, device="cuda")
+
+    def run(flag):
+        old = Fn.set_recompute_depthwise(flag)
+        try:
+            for p in m.parameters():
+                p.grad = None
+            torch.cuda.synchronize()
+            torch.cuda.reset_peak_memory_stats()
+            base = torch.cuda.memory_allocated()
+            y = m(x)
+            held = torch.cuda.memory_allocated() - base      # activations the backward keeps alive
+            y.square().sum().backward()
+            torch.cuda.synchronize()
+            return [p.grad.clone() for p in m.parameters()], held
+        finally:
+            Fn.set_recompute_depthwise(old)
+
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g0, held0 = run(False)
+    m.load_state_dict(sd)                                     # same running statistics for the second pass
+    g1, held1 = run(True)
+    for a, b, (n, _) in zip(g0, g1, m.named_parameters()):
+        if "pointwise.weight" in n:                           # split-K merge by fp32 atomics: order-dependent in the last bits
+            assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-6), n
+        else:
+            assert torch.equal(a, b) or (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-6), n
+    assert held1 < 0.75 * held0, (held0, held1)
+    assert not Fn.get_recompute_depthwise()
