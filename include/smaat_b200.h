@@ -90,6 +90,10 @@ int smaat_pw1x1_fwd(const float* x, const float* w, const float* w_lo,
  * smaat_dw3x3_fwd + smaat_pw1x1_fwd.  smaat_dsconv_eligible returns 1/0 for the same test. */
 int smaat_dsconv_eligible(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
                           const float* pw_w, int H, int W, int k, int Cout);
+/* Same test with the batch-statistics request made explicit: `with_stats` != 0 asks for the kernel that accumulates the
+ * per-channel sum / sum of squares of its output (train-mode BatchNorm, parts_ds.py:25,34) -- the shared-memory-operand kernel. */
+int smaat_dsconv_eligible2(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
+                           const float* pw_w, int H, int W, int k, int Cout, int with_stats);
 int smaat_dsconv_fwd(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
                      const float* dw_w, const float* dw_b, const float* pw_w, const float* pw_w_lo,
                      const float* scale, const float* shift, float* y, int64_t y_bstride, double* stats,
@@ -114,6 +118,10 @@ int smaat_set_dsconv_impl(int impl);
 int smaat_debug_dsconv_timing(unsigned long long* out);
 /* Same for the TMEM-operand kernel (24 counters; layout in csrc/dsconv_tmem.cu). */
 int smaat_debug_dsconv_tmem_timing(unsigned long long* out);
+/* Per-CTA (start ns, end ns, SM id) of the last timed launch of the TMEM-operand kernel: 3 * n_ctas entries, n_ctas <= 256. */
+int smaat_debug_dsconv_tmem_cta_timing(unsigned long long* out, int n_ctas);
+/* Event trace of CTA 0 (launch made with SMAAT_DSCONV_TIMING=2): 16 clock64 stamps per unit, n_units <= 256 (layout in the .cu). */
+int smaat_debug_dsconv_tmem_trace(long long* out, int n_units);
 
 /* 1 if this (x, w, K, Cout, P) can take the tcgen05 path (P % 4 == 0, K % 4 == 0, 16-byte aligned
  * pointers, Cout >= 8), else 0: the caller then uses SMAAT_PW_FP32_SIMT. */

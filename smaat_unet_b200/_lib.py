@@ -23,10 +23,13 @@ SIGNATURES = {
     "smaat_pw1x1_fwd": [_p, _p, _p, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _p],
     "smaat_pw1x1_tc_eligible": [_p, _p, _i, _i, _i],
     "smaat_dsconv_eligible": [_p, _i, _l, _p, _i, _l, _p, _i, _i, _i, _i],
+    "smaat_dsconv_eligible2": [_p, _i, _l, _p, _i, _l, _p, _i, _i, _i, _i, _i],
     "smaat_dsconv_fwd": [_p, _i, _l, _p, _i, _l, _p, _p, _p, _p, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "smaat_debug_dsconv_timing": [_p],
     "smaat_set_dsconv_impl": [_i],
     "smaat_debug_dsconv_tmem_timing": [_p],
+    "smaat_debug_dsconv_tmem_cta_timing": [_p, _i],
+    "smaat_debug_dsconv_tmem_trace": [_p, _i],
     "smaat_dsconv_outconv_fwd": [_p, _i, _l, _p, _i, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "smaat_split_tf32": [_p, _p, _p, _l, _p],
     "smaat_bn_fold": [_p, _p, _p, _p, _p, _f, _p, _p, _i, _p],

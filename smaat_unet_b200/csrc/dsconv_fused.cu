@@ -579,12 +579,18 @@ extern "C" int smaat_set_dsconv_impl(int impl) {
   return SMAAT_OK;
 }
 
-extern "C" int smaat_dsconv_eligible(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
-                                     const float* pw_w, int H, int W, int k, int Cout) {
+extern "C" int smaat_dsconv_eligible2(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
+                                      const float* pw_w, int H, int W, int k, int Cout, int with_stats) {
   const int impl = ds_impl();
-  if (impl != 1 && dsconv_tmem_eligible(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, nullptr, H, W, k, Cout)) return 1;
+  // batch statistics in the epilogue exist in the shared-memory-operand kernel only
+  if (impl != 1 && !with_stats && dsconv_tmem_eligible(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, nullptr, H, W, k, Cout)) return 1;
   if (impl == 2) return 0;
   return ds_eligible(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, nullptr, H, W, k, Cout) ? 1 : 0;
+}
+
+extern "C" int smaat_dsconv_eligible(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride,
+                                     const float* pw_w, int H, int W, int k, int Cout) {
+  return smaat_dsconv_eligible2(x0, C0, x0_bstride, x1, C1, x1_bstride, pw_w, H, W, k, Cout, 0);
 }
 
 static int dsconv_run(const float* x0, int C0, int64_t x0_bstride, const float* x1, int C1, int64_t x1_bstride, const float* dw_w,

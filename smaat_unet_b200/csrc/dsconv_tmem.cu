@@ -45,6 +45,21 @@ namespace smaat {
 // accumulators  [10] drain + store  [11] pairs | [12] kernel cycles | [13] TMA: wait free input stage  [14] units |
 // [15] stager: wait free stage  [16] total  [17] units | [18] weight loader: wait free stage  [19] units
 __device__ unsigned long long g_dt_timing[24];
+// Per-CTA record of the last timed launch (SMAAT_DSCONV_TIMING=1): [3 * cta + 0] globaltimer ns at role dispatch, [+1] at exit,
+// [+2] SM id -- the spread shows how evenly the static pair -> CTA assignment finishes (smaat_debug_dsconv_tmem_cta_timing).
+// Event trace of CTA 0 (SMAAT_DSCONV_TIMING=2; stage-timer atomics off): clock64 at [16 * unit + k] for the first DT_TRACE_UNITS
+// units -- k: 0 TMA box issued  1 producer: box landed  2 stencil done  3 A stage free  4 A stored + arrived |
+// 5 issuer: operands seen  6 half-0 batch starts  7 half-0 batch issued  8 half-1 starts  9 half-1 issued + commits |
+// epilogue (at the pair's first unit): 10 half-0 accumulator seen  11 half-0 drained  12 half-1 seen  13 half-1 drained
+constexpr int DT_TRACE_UNITS = 256;
+__device__ long long g_dt_trace[16 * DT_TRACE_UNITS];
+constexpr int DT_MAX_CTAS = 256;
+__device__ unsigned long long g_dt_cta[3 * DT_MAX_CTAS];
+__device__ __forceinline__ unsigned long long dt_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 struct DtParams {
   const float* dw_w;
@@ -58,7 +73,10 @@ struct DtParams {
   float* oc_y;
   int C0, C1, H, W, Cout, relu, K;
   int px_tiles, py_tiles, total_pairs, nchunks;
-  int flags;           // tuning experiments (SMAAT_DT_FLAGS): bit 0 = no L2 prefetch of the next pair's boxes
+  int flags;           // tuning experiments (SMAAT_DT_FLAGS): 1 = no L2 prefetch of the next pair's boxes; knock-outs that give WRONG
+                       // results and exist to find the binding stage: 2 = epilogue drains but does not store, 4 = producers skip the
+                       // stencil, 8 = issuer skips the two tf32x3 correction MMAs, 16 = issuer issues no MMA, 32 = every input box is
+                       // the CTA's first one (L2 hits).  64 = two issuing warps (half tile 0: warp 1, half tile 1: warp 3)
   int npass;           // output-channel passes of N_TILE channels each (Cout > 128: the depthwise work is repeated per pass)
   int timing;
 };
@@ -173,11 +191,11 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
     }
     for (int s = 0; s < AS; ++s) {
       mbar_init(&a_full[s], 128);
-      mbar_init(&a_empty[s], 1);
+      mbar_init(&a_empty[s], (p.flags & 64) ? 2 : 1);
     }
     for (int s = 0; s < BS; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
+      mbar_init(&b_empty[s], (p.flags & 64) ? 2 : 1);
     }
     for (int s = 0; s < 4; ++s) mbar_init(&tmem_full[s], 1);
     for (int s = 0; s < 4; ++s) mbar_init(&tmem_empty[s], 128);
@@ -211,8 +229,12 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t a_ring = tmem_base + (uint32_t)L::ACC_COLS;
-  const bool rec0 = p.timing && blockIdx.x == 0 && lane == 0;     // stage timers: CTA 0, one lane per role
+  const bool rec0 = p.timing == 1 && blockIdx.x == 0 && lane == 0;     // stage timers: CTA 0, one lane per role
+  const bool trc = p.timing == 2 && blockIdx.x == 0 && lane == 0;
+#define DT_TR(unit, k) do { if (trc && (unit) < (uint32_t)DT_TRACE_UNITS) g_dt_trace[16 * (unit) + (k)] = clock64(); } while (0)
   const long long t_kernel0 = (rec0 && warp == 0) ? clock64() : 0;
+  const bool rec_cta = p.timing && threadIdx.x == 0 && blockIdx.x < DT_MAX_CTAS;
+  if (rec_cta) g_dt_cta[3 * blockIdx.x] = dt_globaltimer();
 #define DT_T(var) const long long var = rec0 ? clock64() : 0
 #define DT_ADD(idx, a, b) do { if (rec0) atomicAdd(&g_dt_timing[idx], (unsigned long long)((b) - (a))); } while (0)
 #define DT_INC(idx) do { if (rec0) atomicAdd(&g_dt_timing[idx], 1ull); } while (0)
@@ -235,7 +257,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
       for (int j = 0; j < my_pairs; ++j) {
         const int pair = blockIdx.x + j * gridDim.x;
         int b, x0, y0;
-        pair_origin(pair, b, x0, y0);
+        pair_origin((p.flags & 32) ? (int)blockIdx.x : pair, b, x0, y0);
         int nb = 0, nx0 = 0, ny0 = 0;
         const bool has_next = j + 1 < my_pairs;
         if (has_next) pair_origin(pair + gridDim.x, nb, nx0, ny0);
@@ -246,6 +268,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
           DT_T(tq1);
           DT_ADD(13, tq0, tq1);
           DT_INC(14);
+          DT_TR(u, 0);
           mbar_arrive_expect_tx(&in_full[s], L::IN_BYTES);
           const int cb = i * CC;
           const CUtensorMap* m = (cb < p.C0) ? &map_in0 : &map_in1;
@@ -282,8 +305,13 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
+  } else if (warp == 1 || (warp == 3 && (p.flags & 64))) {
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues (flag 64: warp 1 takes half tile 0, warp 3 half tile 1) =====
+    const bool dual = (p.flags & 64) != 0;
+    const int h_lo = dual ? (warp == 3 ? 1 : 0) : 0, h_hi = dual ? h_lo + 1 : 2;
+    const bool rec0_role = rec0;
+    const bool rec0 = rec0_role && warp == 1;          // stage timers: the first issuer only
+    const bool skip_corr = (p.flags & 8) != 0, skip_all = (p.flags & 16) != 0;
     constexpr uint32_t idesc = make_idesc_tf32_ts(N_TILE);
     // The waits for unit u + 1's operands are taken BETWEEN the two half-tile batches of unit u: a barrier test costs the
     // issuing thread ~100-200 cycles even when the data is there, and its MMA queue is short -- taken in front of a unit's first
@@ -298,6 +326,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
       DT_ADD(4, tm0, tm1);
       DT_ADD(5, tm1, tm2);
       DT_INC(8);
+      if (warp == 1) DT_TR(uu, 5);
     };
     uint32_t u = 0;
     if (total_units > 0) wait_operands(0);
@@ -308,12 +337,12 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
         const int sa = u % AS, sb = u % BS;
         const int kc = min(TC_BK, p.K - i * TC_BK);
         const int nk = (kc + 7) >> 3;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = h_lo; h < h_hi; ++h) {
           DT_T(tm3);
           if (i == 0) mbar_wait(&tmem_empty[pb * 2 + h], (use & 1u) ^ 1u);     // the epilogue drained this accumulator
           DT_T(tm4);
           DT_ADD(6, tm3, tm4);
+          DT_TR(u, 6 + 2 * h);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t d_tmem = tmem_base + (pb * 2 + h) * N_TILE;
@@ -324,8 +353,9 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
             // k-step: 8 TMEM columns of A, 8 tf32 = 32 B along the K-major weight rows (descriptor address unit = 16 B)
             auto kstep = [&](int kk) {
               const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
+              if (skip_all) return;
               umma_tf32_ts(d_tmem, a_hi + 8u * kk, bd_hi + (uint64_t)(kk * 2), idesc, acc);
-              if (X3) {
+              if (X3 && !skip_corr) {
                 umma_tf32_ts(d_tmem, a_hi + 8u * kk, bd_lo + (uint64_t)(kk * 2), idesc, 1u);
                 umma_tf32_ts(d_tmem, a_hi + 32u + 8u * kk, bd_hi + (uint64_t)(kk * 2), idesc, 1u);
               }
@@ -337,7 +367,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
               for (int kk = 0; kk < nk; ++kk) kstep(kk);
             }
             if (i == nch - 1) umma_commit(&tmem_full[pb * 2 + h]);      // a commit tracks all MMAs issued so far by this thread
-            if (h == 1) {
+            if (h == h_hi - 1) {
               umma_commit(&a_empty[sa]);
               umma_commit(&b_empty[sb]);
             }
@@ -345,7 +375,8 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
           __syncwarp();
           DT_T(tm5);
           DT_ADD(7, tm4, tm5);
-          if (h == 0 && u + 1 < total_units) wait_operands(u + 1);
+          DT_TR(u, 7 + 2 * h);
+          if (h == h_lo && u + 1 < total_units) wait_operands(u + 1);
         }
       }
     }
@@ -370,57 +401,72 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
         mbar_wait(&tmem_full[pb * 2 + h], use & 1u);
         DT_T(te1);
         if (warp == 4) DT_ADD(9, te0, te1);
+        if (warp == 4) DT_TR((uint32_t)j * (uint32_t)nch, 10 + 2 * h);
         tc_fence_after();
         const int gy = y0 + RQ * q + 2 * cy + h, gx = x0 + 4 * cx + r;
         const bool pvalid = (gy < p.H) && (gx < p.W);
         float* ypix = p.y + (int64_t)b * p.y_bstride + (int64_t)gy * p.W + gx;
         float oc_dot = 0.f;
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (pb * 2 + h) * N_TILE;
-#pragma unroll 1
-        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-          if (n0 + c0 >= p.Cout) break;
-          uint32_t v[32];
-          tmem_ld32(tacc + (uint32_t)c0, v);
-          tmem_ld_wait();
-          const int nchn = min(32, p.Cout - (n0 + c0));      // warp-uniform
-          float* yp = ypix + (int64_t)(n0 + c0) * P;
-          const float* sc_p = aff + n0 + c0;                  // the affine of these 32 channels: broadcast LDS.128, 4 channels at a time
-          const float* sh_p = aff + L::AFF_N + n0 + c0;
-          if (p.oc_y) {
-            // channels past Cout: zero accumulators, identity affine, zero OutConv weight -> no mask needed
+        // Accumulator columns in groups of 32, double-buffered in registers: the TMEM load of group g + 1 is in flight while
+        // group g is stored, and the accumulator is handed back to the MMA issuer as soon as its LAST group sits in registers
+        // (before that group's stores) -- with one accumulator buffer per half tile (N_TILE = 128) the drain is exposed.
+        constexpr int NGRP = N_TILE / 32;
+        const int ngrp = min(NGRP, (p.Cout - n0 + 31) >> 5);         // warp-uniform, >= 1
+        const bool no_store = (p.flags & 2) != 0;
+        uint32_t v2[2][32];
+        tmem_ld32(tacc, v2[0]);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 a = *reinterpret_cast<const float4*>(sc_p + 4 * j4), t = *reinterpret_cast<const float4*>(sh_p + 4 * j4);
-              const float4 w4 = *reinterpret_cast<const float4*>(aff + 2 * L::AFF_N + n0 + c0 + 4 * j4);
-              oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), a.x, t.x), act_lo), w4.x, oc_dot);
-              oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), a.y, t.y), act_lo), w4.y, oc_dot);
-              oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), a.z, t.z), act_lo), w4.z, oc_dot);
-              oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), a.w, t.w), act_lo), w4.w, oc_dot);
+        for (int gi = 0; gi < NGRP; ++gi) {
+          if (gi < ngrp) {
+            const int c0 = 32 * gi;
+            uint32_t(&v)[32] = v2[gi & 1];
+            tmem_ld_wait();
+            if (gi + 1 < ngrp) {
+              tmem_ld32(tacc + (uint32_t)(c0 + 32), v2[(gi + 1) & 1]);
+            } else {
+              tc_fence_before();
+              mbar_arrive(&tmem_empty[pb * 2 + h]);
             }
-          } else if (nchn == 32) {
-            // hot path: FFMA, FMNMX, pointer bump, STG per channel; each store instruction of the warp = 128 (2 x 64) contiguous bytes
-            if (pvalid) {
+            const int nchn = min(32, p.Cout - (n0 + c0));      // warp-uniform
+            float* yp = ypix + (int64_t)(n0 + c0) * P;
+            const float* sc_p = aff + n0 + c0;                  // the affine of these 32 channels: broadcast LDS.128, 4 channels at a time
+            const float* sh_p = aff + L::AFF_N + n0 + c0;
+            if (p.oc_y) {
+              // channels past Cout: zero accumulators, identity affine, zero OutConv weight -> no mask needed
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 a = *reinterpret_cast<const float4*>(sc_p + 4 * j4), t = *reinterpret_cast<const float4*>(sh_p + 4 * j4);
-                yp[0] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), a.x, t.x), act_lo);
-                yp[P] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), a.y, t.y), act_lo);
-                yp[2 * P] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), a.z, t.z), act_lo);
-                yp[3 * P] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), a.w, t.w), act_lo);
-                yp += 4 * P;
+                const float4 w4 = *reinterpret_cast<const float4*>(aff + 2 * L::AFF_N + n0 + c0 + 4 * j4);
+                oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), a.x, t.x), act_lo), w4.x, oc_dot);
+                oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), a.y, t.y), act_lo), w4.y, oc_dot);
+                oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), a.z, t.z), act_lo), w4.z, oc_dot);
+                oc_dot = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), a.w, t.w), act_lo), w4.w, oc_dot);
               }
-            }
-          } else {
+            } else if (nchn == 32) {
+              // hot path: FFMA, FMNMX, pointer bump, STG per channel; each store instruction of the warp = 128 (2 x 64) contiguous bytes
+              if (pvalid && !no_store) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (pvalid && j < nchn) yp[(int64_t)j * P] = fmaxf(fmaf(__uint_as_float(v[j]), sc_p[j], sh_p[j]), act_lo);
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 a = *reinterpret_cast<const float4*>(sc_p + 4 * j4), t = *reinterpret_cast<const float4*>(sh_p + 4 * j4);
+                  yp[0] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), a.x, t.x), act_lo);
+                  yp[P] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), a.y, t.y), act_lo);
+                  yp[2 * P] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), a.z, t.z), act_lo);
+                  yp[3 * P] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), a.w, t.w), act_lo);
+                  yp += 4 * P;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (pvalid && j < nchn) yp[(int64_t)j * P] = fmaxf(fmaf(__uint_as_float(v[j]), sc_p[j], sh_p[j]), act_lo);
+            }
           }
         }
         if (p.oc_y && pvalid) p.oc_y[(int64_t)b * P + (int64_t)gy * p.W + gx] = oc_dot + (p.oc_b ? __ldg(p.oc_b) : 0.f);
-        tc_fence_before();
-        mbar_arrive(&tmem_empty[pb * 2 + h]);
         DT_T(te2);
         if (warp == 4) DT_ADD(10, te1, te2);
+        if (warp == 4) DT_TR((uint32_t)j * (uint32_t)nch, 11 + 2 * h);
       }
     }
   } else if (warp >= 8) {
@@ -449,9 +495,18 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
         DT_T(tp0);
         mbar_wait(&in_full[s], (u / IS) & 1u);
         DT_T(tp1);
+        if ((warp & 3) == 0) DT_TR(u, 1);
         const float* in_stage = reinterpret_cast<const float*>(smem + s * L::IN_BYTES);
         const float* wd = reinterpret_cast<const float*>(smem + L::OFF_WD) + (size_t)i * CC * L::WD_FLOATS;
         uint64_t acc[4][2][4];       // [channel i4][half / output row h][pixel] = (depthwise output 2 ci, 2 ci + 1)
+        if (p.flags & 4) {
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int x = 0; x < 4; ++x) acc[i4][h][x] = (uint64_t)(u + x);
+        } else
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
           const int ci = 4 * i4 + ph;
@@ -488,8 +543,10 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
           }
         }
         // the A stage is needed only now: the stencil of this unit overlapped the MMAs still reading the stage
+        if ((warp & 3) == 0) DT_TR(u, 2);
         mbar_wait(&a_empty[sa], ((u / AS) & 1u) ^ 1u);
         DT_T(tp2);
+        if ((warp & 3) == 0) DT_TR(u, 3);
         tc_fence_after();
         const uint32_t a_st = a_ring + (uint32_t)(sa * L::AST_COLS) + lane_base;
 #pragma unroll
@@ -518,6 +575,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
         mbar_arrive(&a_full[sa]);
         mbar_arrive(&in_empty[s]);
         DT_T(tp3);
+        if ((warp & 3) == 0) DT_TR(u, 4);
         if (warp == 8) { DT_ADD(0, tp0, tp1); DT_ADD(1, tp1, tp2); DT_ADD(2, tp2, tp3); DT_INC(3); }
       }
     }
@@ -525,9 +583,16 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
   tc_fence_before();
   __syncthreads();
   if (rec0 && warp == 0) atomicAdd(&g_dt_timing[12], (unsigned long long)(clock64() - t_kernel0));
+  if (rec_cta) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_dt_cta[3 * blockIdx.x + 1] = dt_globaltimer();
+    g_dt_cta[3 * blockIdx.x + 2] = smid;
+  }
 #undef DT_T
 #undef DT_ADD
 #undef DT_INC
+#undef DT_TR
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -648,6 +713,26 @@ int dsconv_tmem_run(const float* x0, int C0, int64_t x0_bstride, const float* x1
 }
 
 }  // namespace smaat
+
+/* Debug hook: the event trace of CTA 0 of the last launch made with SMAAT_DSCONV_TIMING=2 (16 clock64 stamps per unit, layout
+ * at g_dt_trace) for the first `n_units` <= 256 units, to the HOST array `out`.  Synchronises the device. */
+extern "C" int smaat_debug_dsconv_tmem_trace(long long* out, int n_units) {
+  using namespace smaat;
+  SMAAT_REQUIRE(out && n_units > 0 && n_units <= DT_TRACE_UNITS, "debug_dsconv_tmem_trace: bad arguments");
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_dt_trace, sizeof(long long) * 16 * n_units);
+  if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "debug_dsconv_tmem_trace: %s", cudaGetErrorString(e));
+  return SMAAT_OK;
+}
+
+/* Debug hook: per-CTA (start ns, end ns, SM id) triples of the last timed launch of the TMEM-operand kernel, `n_ctas` <= 256 of
+ * them, to the HOST array `out` (3 * n_ctas entries).  Synchronises the device. */
+extern "C" int smaat_debug_dsconv_tmem_cta_timing(unsigned long long* out, int n_ctas) {
+  using namespace smaat;
+  SMAAT_REQUIRE(out && n_ctas > 0 && n_ctas <= DT_MAX_CTAS, "debug_dsconv_tmem_cta_timing: bad arguments");
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_dt_cta, sizeof(unsigned long long) * 3 * n_ctas);
+  if (e != cudaSuccess) return fail(SMAAT_E_CUDA, "debug_dsconv_tmem_cta_timing: %s", cudaGetErrorString(e));
+  return SMAAT_OK;
+}
 
 /* Debug hook: copies the TMEM-operand kernel's stage timers of CTA 0 (24 counters, clock64 cycles; layout above) to the HOST
  * array `out` and clears them.  Synchronises the device. */

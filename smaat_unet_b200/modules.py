@@ -90,6 +90,10 @@ class DepthwiseSeparableConv(_CachingModule):
             self._wsplit_key = None if in_train_capture else key
         return self._wsplit
 
+    def fused_takes(self, x, x1=None, stats=False) -> bool:
+        """Whether the one-kernel depthwise->pointwise path takes this input (shape, alignment, arithmetic mode)."""
+        return ops.dsconv_takes(x, x1, self.pointwise.weight.detach(), self.kernels_per_layer, stats=stats)
+
     def run(self, x, x1=None, scale=None, shift=None, relu=False, in_scale=None, in_shift=None, stats=None, outconv=None):
         """dw -> pw with the pw epilogue y = act(scale * acc + shift).  scale/shift None => (1, pointwise.bias)."""
         self._check()

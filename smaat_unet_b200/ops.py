@@ -198,6 +198,20 @@ def set_dsconv_impl(impl: str) -> None:
     _lib.check(_lib.load().smaat_set_dsconv_impl({"auto": 0, "smem": 1, "tmem": 2}[impl]), "smaat_set_dsconv_impl")
 
 
+def dsconv_takes(x, x1, pw_weight, k, mode=None, stats=False) -> bool:
+    """True when ``dsconv`` would run its fused kernel on these inputs (smaat_dsconv_eligible + the arithmetic mode)."""
+    mode = mode or _pw_mode
+    if not _fuse_ds or PW_MODES[mode] == 0:
+        return False
+    x, bs0 = _nchw_bstride(x, "x")
+    C1, bs1 = 0, 0
+    if x1 is not None:
+        x1, bs1 = _nchw_bstride(x1, "x1")
+        C1 = x1.shape[1]
+    w2d = _dense(pw_weight, "pointwise.weight").view(pw_weight.shape[0], -1)
+    return bool(_lib.load().smaat_dsconv_eligible2(_ptr(x), x.shape[1], bs0, _ptr(x1), C1, bs1, _ptr(w2d), x.shape[2], x.shape[3], k, w2d.shape[0], int(bool(stats))))
+
+
 def dsconv(x, dw_weight, dw_bias, k, pw_weight, scale, shift, relu, x1=None, mode=None, w_split=None, stats=None, outconv=None):
     """Fused DepthwiseSeparableConv (layers.py:47-50) + affine (+ReLU); returns None when the fused kernel
     does not take this shape/mode (caller then runs dw3x3 + pw1x1).  ``outconv=(weight (1, Cout[,1,1]), bias or None)``
@@ -215,7 +229,7 @@ def dsconv(x, dw_weight, dw_bias, k, pw_weight, scale, shift, relu, x1=None, mod
     Cout, K = w2d.shape
     assert K == k * (C0 + C1), f"pointwise weight {tuple(pw_weight.shape)} does not match k*Cin={k * (C0 + C1)}"
     lib = _lib.load()
-    if not lib.smaat_dsconv_eligible(_ptr(x), C0, bs0, _ptr(x1), C1, bs1, _ptr(w2d), H, W, k, Cout):
+    if not lib.smaat_dsconv_eligible2(_ptr(x), C0, bs0, _ptr(x1), C1, bs1, _ptr(w2d), H, W, k, Cout, int(stats is not None)):
         return None
     wlo = None
     if PW_MODES[mode] == 2:
@@ -308,7 +322,7 @@ def upsample2x_pad(x, Ho, Wo):
     x = _dense(x, "x")
     B, Cc, H, W = x.shape
     y = torch.empty((B, Cc, Ho, Wo), device=x.device, dtype=torch.float32)
-    _call("smaat_upsample2x_pad_fwd", 4 * B * Cc * (H * W + Ho * Wo), 0, _lib.load().smaat_upsample2x_pad_fwd, _ptr(x), _ptr(y), Cc * Ho * Wo, B, Cc, H, W, Ho, Wo, _stream())
+    _call(f"smaat_upsample2x_pad_fwd[C{Cc}_S{H}]", 4 * B * Cc * (H * W + Ho * Wo), 0, _lib.load().smaat_upsample2x_pad_fwd, _ptr(x), _ptr(y), Cc * Ho * Wo, B, Cc, H, W, Ho, Wo, _stream())
     return y
 
 
@@ -384,7 +398,7 @@ def cbam_pool_mlp(x, w1, b1, w2, b2, with_maxpool=False):
     sc = torch.empty_like(avg)
     pooled = torch.empty((B, Cc, H // 2, W // 2), device=x.device, dtype=torch.float32) if want_pool else None
     cnt = _counters(x.device, B)
-    _call("smaat_cbam_pool_mlp_fwd", (5 if want_pool else 4) * B * Cc * H * W, 0, _lib.load().smaat_cbam_pool_mlp_fwd, _ptr(x), _ptr(avg), _ptr(mx),
+    _call(f"smaat_cbam_pool_mlp_fwd[C{Cc}_S{H}]", (5 if want_pool else 4) * B * Cc * H * W, 0, _lib.load().smaat_cbam_pool_mlp_fwd, _ptr(x), _ptr(avg), _ptr(mx),
           _ptr(pooled), _ptr(_dense(w1, "w1")), _ptr(b1), _ptr(_dense(w2, "w2")), _ptr(b2), _ptr(sc), _ptr(cnt), B, Cc, H, W, hidden, _stream())
     return sc, avg, mx, pooled
 
@@ -403,7 +417,7 @@ def cbam_gate_scale(x, sc, pooled, wsp, bn_affine, out=None):
     if ybs % 4 != 0 or out.data_ptr() % 16 or x.data_ptr() % 16:
         return None
     ks = wsp.shape[-1]
-    _call("smaat_cbam_gate_scale_fwd", 4 * B * (2 * Cc + 2) * H * W, 0, _lib.load().smaat_cbam_gate_scale_fwd, _ptr(pooled), _ptr(_dense(wsp, "wsp")),
+    _call(f"smaat_cbam_gate_scale_fwd[C{Cc}_S{H}]", 4 * B * (2 * Cc + 2) * H * W, 0, _lib.load().smaat_cbam_gate_scale_fwd, _ptr(pooled), _ptr(_dense(wsp, "wsp")),
           _ptr(bn_affine), _ptr(x), _ptr(sc), _ptr(out), ybs, B, Cc, H, W, ks, _stream())
     return out
 
@@ -420,7 +434,7 @@ def cbam_reduce(x, sc):
     x = _dense(x, "x")
     B, Cc, H, W = x.shape
     pooled = torch.empty((B, 2, H, W), device=x.device, dtype=torch.float32)
-    _call("smaat_cbam_reduce_fwd", 4 * B * (Cc + 2) * H * W, 0, _lib.load().smaat_cbam_reduce_fwd, _ptr(x), _ptr(sc), _ptr(pooled), B, Cc, H * W, _stream())
+    _call(f"smaat_cbam_reduce_fwd[C{Cc}_S{H}]", 4 * B * (Cc + 2) * H * W, 0, _lib.load().smaat_cbam_reduce_fwd, _ptr(x), _ptr(sc), _ptr(pooled), B, Cc, H * W, _stream())
     return pooled
 
 

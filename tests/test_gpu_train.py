@@ -379,9 +379,9 @@ def test_two_phase_backward_is_verified_not_assumed():
         sess.close()
 
 
-def test_recompute_depthwise_is_bit_identical_and_saves_memory():
+def test_recompute_depthwise_matches_and_saves_memory():
     """functional.set_recompute_depthwise drops the depthwise results after the forward and re-runs the same kernel in the
-    backward: gradients are bit-identical (same kernel, same inputs), peak memory of a forward+backward goes down."""
+    backward: gradients agree to the run-to-run noise of the atomically merged reductions (same kernel, same inputs), peak memory of a forward+backward goes down."""
     from smaat_unet_b200 import functional as Fn
     torch.manual_seed(5)
     m = S.SmaAt_UNet(12, 1, kernels_per_layer=2).cuda().train()
@@ -405,12 +405,13 @@ def test_recompute_depthwise_is_bit_identical_and_saves_memory():
 
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     g0, held0 = run(False)
-    m.load_state_dict(sd)                                     # same running statistics for the second pass
+    m.load_state_dict(sd)                                     # same running statistics for every pass
+    g0b, _ = run(False)                                       # run-to-run noise of the fp32-atomic reductions (split-K merges, dw wgrad)
+    m.load_state_dict(sd)
     g1, held1 = run(True)
-    for a, b, (n, _) in zip(g0, g1, m.named_parameters()):
-        if "pointwise.weight" in n:                           # split-K merge by fp32 atomics: order-dependent in the last bits
-            assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-6), n
-        else:
-            assert torch.equal(a, b) or (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-6), n
+    gmax = max(a.abs().max().item() for a in g0)
+    for a, a2, b, (n, _) in zip(g0, g0b, g1, m.named_parameters()):
+        noise = (a - a2).abs().max().item()
+        assert (a - b).abs().max().item() <= 10 * noise + 1e-6 * gmax, (n, noise, gmax)
     assert held1 < 0.75 * held0, (held0, held1)
     assert not Fn.get_recompute_depthwise()
