@@ -303,15 +303,9 @@ __device__ __forceinline__ float up_adj_weight(int u, int t, int n, float r) {
   return (i0 == t ? 1.f - l : 0.f) + (i1 == t ? l : 0.f);
 }
 
-constexpr int UB_TW = 2 * UB_TX + 4;   // upsampled columns a tile of UB_TX source columns can touch (6 taps, stride 2)
-
-// dx = adjoint of (bilinear x2, align_corners=True, then zero pad): every source pixel gathers <= 6 x 6 upsampled gradients.
-// The dy tile is staged in shared memory by coalesced loads first (the first version read it with six stride-2 loads per
-// output: 1.4 TB/s), then the separable adjoint runs out of shared memory: horizontal 6 taps, vertical 6 taps.
 __global__ void __launch_bounds__(256) upsample2x_pad_bwd_kernel(const float* __restrict__ dy, int64_t dy_bstride,
                                                                  float* __restrict__ dx, int C, int H, int W, int Ho, int Wo,
                                                                  int pad_t, int pad_l, float ry, float rx, int tiles_x) {
-  __shared__ float tile[UB_ROWS][UB_TW + 1];
   __shared__ float hs[UB_ROWS][UB_TX + 1];
   __shared__ float wys[UB_TY][6];
   const int c = blockIdx.y, b = blockIdx.z;
@@ -319,31 +313,33 @@ __global__ void __launch_bounds__(256) upsample2x_pad_bwd_kernel(const float* __
   const int y0 = ty * UB_TY, x0 = tx * UB_TX;
   const float* g = dy + (int64_t)b * dy_bstride + (int64_t)c * Ho * Wo + (int64_t)pad_t * Wo + pad_l;
   const int col = threadIdx.x & (UB_TX - 1), rgrp = threadIdx.x / UB_TX;   // 4 row groups
-  const int x = x0 + col;
-  const int r0 = 2 * y0 - 2, c0 = 2 * x0 - 2;   // first upsampled row / column this tile needs
-  for (int idx = threadIdx.x; idx < UB_ROWS * UB_TW; idx += 256) {
-    const int r = idx / UB_TW, cc = idx - r * UB_TW;
-    const int uy = r0 + r, ux = c0 + cc;
-    tile[r][cc] = (uy >= 0 && uy < 2 * H && ux >= 0 && ux < 2 * W) ? __ldg(g + (int64_t)uy * Wo + ux) : 0.f;
-  }
+  const int x = min(x0 + col, W - 1);   // columns past the edge recompute the last one (never stored)
+  const int u0 = 2 * x - 2;
+  // out-of-range taps get weight 0 and a clamped (valid) address: no predicates in the row loop
   float wx[6];
+  int ox[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) wx[i] = up_adj_weight(2 * x - 2 + i, x, W, rx);
+  for (int i = 0; i < 6; ++i) {
+    wx[i] = up_adj_weight(u0 + i, x, W, rx);
+    ox[i] = min(max(u0 + i, 0), 2 * W - 1);
+  }
   if (threadIdx.x < UB_TY * 6) {
     const int yy = threadIdx.x / 6, i = threadIdx.x - yy * 6;
     const int y = y0 + yy;
     wys[yy][i] = (y < H) ? up_adj_weight(2 * y - 2 + i, y, H, ry) : 0.f;
   }
-  __syncthreads();
+  const int r0 = 2 * y0 - 2;   // first upsampled row this tile needs
 #pragma unroll 3
   for (int r = rgrp; r < UB_ROWS; r += 256 / UB_TX) {
+    const int uy = min(max(r0 + r, 0), 2 * H - 1);   // rows outside the image only meet zero vertical weights
+    const float* row = g + (int64_t)uy * Wo;
     float a = 0.f;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) a = fmaf(wx[i], tile[r][2 * col + i], a);
+    for (int i = 0; i < 6; ++i) a = fmaf(wx[i], __ldg(row + ox[i]), a);
     hs[r][col] = a;
   }
   __syncthreads();
-  if (x >= W) return;
+  if (x0 + col >= W) return;
   float* dst = dx + ((int64_t)b * C + c) * H * W;
 #pragma unroll
   for (int yy = rgrp; yy < UB_TY; yy += 256 / UB_TX) {

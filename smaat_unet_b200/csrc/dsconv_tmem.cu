@@ -37,6 +37,13 @@
 
 #include "tc_common.cuh"
 
+// Instrumentation (stage timers, event trace, knock-out flags) is compiled in only with -DSMAAT_DT_INSTRUMENT=1
+// (SMAAT_DT_INSTRUMENT=1 bash build.sh): even predicated off, its instructions sat in the single-lane MMA issue loop, whose
+// length -- not the tensor pipe -- set the pace of the kernel (profiles/r02_dsconv_tmem_trace.txt).
+#ifndef SMAAT_DT_INSTRUMENT
+#define SMAAT_DT_INSTRUMENT 0
+#endif
+
 namespace smaat {
 
 // Stage timers of CTA 0 (clock64 cycles, accumulated over launches until read; SMAAT_DSCONV_TIMING=1): see
@@ -73,10 +80,11 @@ struct DtParams {
   float* oc_y;
   int C0, C1, H, W, Cout, relu, K;
   int px_tiles, py_tiles, total_pairs, nchunks;
-  int flags;           // tuning experiments (SMAAT_DT_FLAGS): 1 = no L2 prefetch of the next pair's boxes; knock-outs that give WRONG
+  int flags;           // tuning experiments (SMAAT_DT_FLAGS): 1 = L2 prefetch of the next pair's boxes (measured 3 % slower: off);
+                       // 64 = one MMA-issuing warp instead of two (2.5 % slower).  Instrumented builds only, knock-outs that give WRONG
                        // results and exist to find the binding stage: 2 = epilogue drains but does not store, 4 = producers skip the
                        // stencil, 8 = issuer skips the two tf32x3 correction MMAs, 16 = issuer issues no MMA, 32 = every input box is
-                       // the CTA's first one (L2 hits).  64 = two issuing warps (half tile 0: warp 1, half tile 1: warp 3)
+                       // the CTA's first one (L2 hits)
   int npass;           // output-channel passes of N_TILE channels each (Cout > 128: the depthwise work is repeated per pass)
   int timing;
 };
@@ -129,7 +137,7 @@ struct DtCfg {
   static constexpr int WD_MAX_BYTES = WD_MAXC * WD_FLOATS * 4;   // nchunks * 16 rows of 80 B at the END of the carve-up (run-time size)
   static constexpr int B_BYTES = N_TILE * TC_BK * 4;
   static constexpr int BST_BYTES = (X3 ? 2 : 1) * B_BYTES;
-  static constexpr int NG = 2;                            // producer groups (128 threads each)
+  static constexpr int NG = BIG ? 2 : 3;                  // producer groups (128 threads each); BIG: no room for a fourth input stage
   // TMEM: accumulators [pair buffer][half] x N_TILE columns, then the A ring (per stage: half 0 hi | lo, half 1 hi | lo)
   static constexpr int ACC_PAIRS = (N_TILE <= 64) ? 2 : 1;
   static constexpr int ACC_COLS = ACC_PAIRS * 2 * N_TILE;
@@ -138,8 +146,8 @@ struct DtCfg {
   static constexpr int AS = ((512 - ACC_COLS) / AST_COLS) > 4 ? 4 : ((512 - ACC_COLS) / AST_COLS);
   static_assert(AS >= 2, "A ring");
   // BIG (more than 256 input channels: 40 KB of depthwise weights, >= 16 chunks per pair) trades ring depth for the table
-  static constexpr int BS = BIG ? 2 : 3;                  // pointwise-weight ring: its TMA loads must cover an L2 round trip
-  static constexpr int IS = (N_TILE <= 64 && !BIG) ? 5 : 3;   // input ring (the TMA thread runs far ahead of the producers anyway)
+  static constexpr int BS = (BIG || N_TILE > 64) ? 2 : 3; // pointwise-weight ring: its TMA loads must cover an L2 round trip
+  static constexpr int IS = BIG ? 3 : (N_TILE <= 64 ? 5 : 4);   // input ring: every producer group holds a stage while it works, + >= 1 in flight
   static_assert(IS >= 2, "input ring");
   static constexpr int OFF_BR = ((IS * IN_BYTES + 1023) / 1024) * 1024;
   static constexpr int OFF_BAR = OFF_BR + BS * BST_BYTES;
@@ -191,11 +199,11 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
     }
     for (int s = 0; s < AS; ++s) {
       mbar_init(&a_full[s], 128);
-      mbar_init(&a_empty[s], (p.flags & 64) ? 2 : 1);
+      mbar_init(&a_empty[s], (p.flags & 64) ? 1 : 2);
     }
     for (int s = 0; s < BS; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], (p.flags & 64) ? 2 : 1);
+      mbar_init(&b_empty[s], (p.flags & 64) ? 1 : 2);
     }
     for (int s = 0; s < 4; ++s) mbar_init(&tmem_full[s], 1);
     for (int s = 0; s < 4; ++s) mbar_init(&tmem_empty[s], 128);
@@ -229,11 +237,12 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t a_ring = tmem_base + (uint32_t)L::ACC_COLS;
-  const bool rec0 = p.timing == 1 && blockIdx.x == 0 && lane == 0;     // stage timers: CTA 0, one lane per role
-  const bool trc = p.timing == 2 && blockIdx.x == 0 && lane == 0;
+  const bool rec0 = SMAAT_DT_INSTRUMENT && p.timing == 1 && blockIdx.x == 0 && lane == 0;     // stage timers: CTA 0, one lane per role
+  const bool trc = SMAAT_DT_INSTRUMENT && p.timing == 2 && blockIdx.x == 0 && lane == 0;
+#define DT_FLAG(x) (SMAAT_DT_INSTRUMENT && (p.flags & (x)))
 #define DT_TR(unit, k) do { if (trc && (unit) < (uint32_t)DT_TRACE_UNITS) g_dt_trace[16 * (unit) + (k)] = clock64(); } while (0)
   const long long t_kernel0 = (rec0 && warp == 0) ? clock64() : 0;
-  const bool rec_cta = p.timing && threadIdx.x == 0 && blockIdx.x < DT_MAX_CTAS;
+  const bool rec_cta = SMAAT_DT_INSTRUMENT && p.timing && threadIdx.x == 0 && blockIdx.x < DT_MAX_CTAS;
   if (rec_cta) g_dt_cta[3 * blockIdx.x] = dt_globaltimer();
 #define DT_T(var) const long long var = rec0 ? clock64() : 0
 #define DT_ADD(idx, a, b) do { if (rec0) atomicAdd(&g_dt_timing[idx], (unsigned long long)((b) - (a))); } while (0)
@@ -252,12 +261,14 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
 
   if (warp == 0) {
     // ===== TMA: one input halo box per unit =====
+    // [lane test, not elect.sync: with elect.sync here (and in the weight loader) the many-chunk concat case of
+    // tests/test_gpu_kernels.py produced wrong results; these loops issue 1-3 instructions per unit, nothing to gain]
     if (lane == 0) {
       uint32_t u = 0;
       for (int j = 0; j < my_pairs; ++j) {
         const int pair = blockIdx.x + j * gridDim.x;
         int b, x0, y0;
-        pair_origin((p.flags & 32) ? (int)blockIdx.x : pair, b, x0, y0);
+        pair_origin(DT_FLAG(32) ? (int)blockIdx.x : pair, b, x0, y0);
         int nb = 0, nx0 = 0, ny0 = 0;
         const bool has_next = j + 1 < my_pairs;
         if (has_next) pair_origin(pair + gridDim.x, nb, nx0, ny0);
@@ -279,7 +290,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(&in_full[s])), "r"(x0 - 4), "r"(y0 - 1), "r"(cc), "r"(b)
               : "memory");
           // the same chunk of this CTA's NEXT pair goes to L2 now, so its TMA load later pays L2 latency only
-          if (has_next && !(p.flags & 1))
+          if (has_next && (p.flags & 1))
             asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
                          "r"(nx0 - 4), "r"(ny0 - 1), "r"(cc), "r"(nb)
                          : "memory");
@@ -305,81 +316,124 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
         }
       }
     }
-  } else if (warp == 1 || (warp == 3 && (p.flags & 64))) {
-    // ===== MMA issuer: warp-uniform loop, one elected lane issues (flag 64: warp 1 takes half tile 0, warp 3 half tile 1) =====
-    const bool dual = (p.flags & 64) != 0;
-    const int h_lo = dual ? (warp == 3 ? 1 : 0) : 0, h_hi = dual ? h_lo + 1 : 2;
-    const bool rec0_role = rec0;
-    const bool rec0 = rec0_role && warp == 1;          // stage timers: the first issuer only
-    const bool skip_corr = (p.flags & 8) != 0, skip_all = (p.flags & 16) != 0;
-    constexpr uint32_t idesc = make_idesc_tf32_ts(N_TILE);
-    // The waits for unit u + 1's operands are taken BETWEEN the two half-tile batches of unit u: a barrier test costs the
-    // issuing thread ~100-200 cycles even when the data is there, and its MMA queue is short -- taken in front of a unit's first
-    // MMA (as the first version did) they left the tensor pipe idle ~350 cycles per unit.
-    const uint32_t total_units = (uint32_t)my_pairs * (uint32_t)nch;
-    auto wait_operands = [&](uint32_t uu) {
-      DT_T(tm0);
-      mbar_wait(&a_full[uu % AS], (uu / AS) & 1u);
-      DT_T(tm1);
-      mbar_wait(&b_full[uu % BS], (uu / BS) & 1u);
-      DT_T(tm2);
-      DT_ADD(4, tm0, tm1);
-      DT_ADD(5, tm1, tm2);
-      DT_INC(8);
-      if (warp == 1) DT_TR(uu, 5);
-    };
-    uint32_t u = 0;
-    if (total_units > 0) wait_operands(0);
-    for (int j = 0; j < my_pairs; ++j) {
-      const uint32_t pb = (L::ACC_PAIRS == 2) ? (uint32_t)(j & 1) : 0u;
-      const uint32_t use = (L::ACC_PAIRS == 2) ? (uint32_t)(j >> 1) : (uint32_t)j;    // how often this pair buffer was used before
-      for (int i = 0; i < nch; ++i, ++u) {
-        const int sa = u % AS, sb = u % BS;
-        const int kc = min(TC_BK, p.K - i * TC_BK);
-        const int nk = (kc + 7) >> 3;
-        for (int h = h_lo; h < h_hi; ++h) {
-          DT_T(tm3);
-          if (i == 0) mbar_wait(&tmem_empty[pb * 2 + h], (use & 1u) ^ 1u);     // the epilogue drained this accumulator
-          DT_T(tm4);
-          DT_ADD(6, tm3, tm4);
-          DT_TR(u, 6 + 2 * h);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t d_tmem = tmem_base + (pb * 2 + h) * N_TILE;
-            const uint32_t a_hi = a_ring + (uint32_t)(sa * L::AST_COLS + h * L::AH_COLS);
-            const uint32_t b_addr = smem_u32(b_base + sb * L::BST_BYTES);
-            const uint64_t bd_hi = make_b_desc(b_addr);
-            const uint64_t bd_lo = make_b_desc(b_addr + L::B_BYTES);
-            // k-step: 8 TMEM columns of A, 8 tf32 = 32 B along the K-major weight rows (descriptor address unit = 16 B)
-            auto kstep = [&](int kk) {
-              const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
-              if (skip_all) return;
-              umma_tf32_ts(d_tmem, a_hi + 8u * kk, bd_hi + (uint64_t)(kk * 2), idesc, acc);
-              if (X3 && !skip_corr) {
-                umma_tf32_ts(d_tmem, a_hi + 8u * kk, bd_lo + (uint64_t)(kk * 2), idesc, 1u);
-                umma_tf32_ts(d_tmem, a_hi + 32u + 8u * kk, bd_hi + (uint64_t)(kk * 2), idesc, 1u);
-              }
-            };
-            if (nk == TC_BK / 8) {
-#pragma unroll
-              for (int kk = 0; kk < TC_BK / 8; ++kk) kstep(kk);      // the common case: MMAs back to back
-            } else {
-              for (int kk = 0; kk < nk; ++kk) kstep(kk);
-            }
-            if (i == nch - 1) umma_commit(&tmem_full[pb * 2 + h]);      // a commit tracks all MMAs issued so far by this thread
-            if (h == h_hi - 1) {
-              umma_commit(&a_empty[sa]);
-              umma_commit(&b_empty[sb]);
-            }
+  } else if (warp == 1 || (warp == 3 && !(p.flags & 64))) {
+    // ===== MMA issuers: ONE lane of warp 1 (half tile 0) and of warp 3 (half tile 1) run the loop; flag 64: warp 1 takes both =====
+    // A lone warp issues its dependent scalar instructions a few cycles apart, so the loop is kept to the MMAs, their operand
+    // addresses, the commits and the barrier tests: the first version (elect.sync per batch, index arithmetic by division,
+    // predicated-off timers) spent ~550 instructions ~ 2000 cycles per unit here while the 24 MMAs need 800-1600.
+    // The waits for unit u + 1's operands are taken BETWEEN the two half-tile batches of unit u (behind queued MMAs).
+    if (elect_one()) {      // elect.sync, not lane == 0: the compiler then knows ONE thread runs the region and emits each
+                            // tcgen05.mma once -- under a plain lane test every MMA sits in its own per-active-lane loop
+      constexpr uint32_t idesc = make_idesc_tf32_ts(N_TILE);
+      const bool dual = (p.flags & 64) == 0;
+      const bool rec0_role = rec0;
+      const bool rec0 = rec0_role && warp == 1;          // stage timers: the first issuer only
+      const uint32_t total_units = (uint32_t)my_pairs * (uint32_t)nch;
+      const int nk_last = (min(TC_BK, p.K - (nch - 1) * TC_BK) + 7) >> 3;
+      const uint64_t bdesc0 = make_b_desc(smem_u32(b_base));          // stage sb: + sb * BST_BYTES / 16 in the address field
+      uint32_t u = 0, sa = 0, sb = 0, pha = 0, phb = 0;               // ring positions and phase bits of the CURRENT unit
+      // one half-tile batch of unit (sa, sb): 4 k-steps x (hi*hi [+ hi*lo + lo*hi])
+      auto batch = [&](uint32_t h, uint32_t pb, int i, int nk) {
+        const uint32_t d_tmem = tmem_base + (pb * 2 + h) * N_TILE;
+        const uint32_t a_hi = a_ring + sa * (uint32_t)L::AST_COLS + h * (uint32_t)L::AH_COLS;
+        const uint64_t bd_hi = bdesc0 + (uint64_t)(sb * (uint32_t)(L::BST_BYTES >> 4));
+        const uint64_t bd_lo = bd_hi + (uint64_t)(L::B_BYTES >> 4);
+        // k-step: 8 TMEM columns of A, 8 tf32 = 32 B along the K-major weight rows (descriptor address unit = 16 B)
+        auto kstep = [&](int kk, uint32_t acc) {
+          if (DT_FLAG(16)) return;
+          umma_tf32_ts(d_tmem, a_hi + 8u * kk, bd_hi + (uint64_t)(kk * 2), idesc, acc);
+          if (X3 && !DT_FLAG(8)) {
+            umma_tf32_ts(d_tmem, a_hi + 8u * kk, bd_lo + (uint64_t)(kk * 2), idesc, 1u);
+            umma_tf32_ts(d_tmem, a_hi + 32u + 8u * kk, bd_hi + (uint64_t)(kk * 2), idesc, 1u);
           }
-          __syncwarp();
-          DT_T(tm5);
-          DT_ADD(7, tm4, tm5);
-          DT_TR(u, 7 + 2 * h);
-          if (h == h_lo && u + 1 < total_units) wait_operands(u + 1);
+        };
+        if (nk == TC_BK / 8) {      // the common case: MMAs back to back
+          kstep(0, i > 0 ? 1u : 0u);
+          kstep(1, 1u);
+          kstep(2, 1u);
+          kstep(3, 1u);
+        } else {
+          for (int kk = 0; kk < nk; ++kk) kstep(kk, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+      };
+      auto wait_next = [&]() {      // operands of unit u + 1
+        const uint32_t san = (sa + 1 == (uint32_t)AS) ? 0u : sa + 1, sbn = (sb + 1 == (uint32_t)BS) ? 0u : sb + 1;
+        DT_T(tm0);
+        mbar_wait(&a_full[san], san ? pha : pha ^ 1u);
+        DT_T(tm1);
+        mbar_wait(&b_full[sbn], sbn ? phb : phb ^ 1u);
+        DT_T(tm2);
+        tc_fence_after();
+        DT_ADD(4, tm0, tm1);
+        DT_ADD(5, tm1, tm2);
+        DT_INC(8);
+        if (warp == 1) DT_TR(u + 1, 5);
+      };
+      if (total_units > 0) {
+        mbar_wait(&a_full[0], 0u);
+        mbar_wait(&b_full[0], 0u);
+        tc_fence_after();
+      }
+      const uint32_t hmine = (warp == 3) ? 1u : 0u;
+      for (int j = 0; j < my_pairs; ++j) {
+        const uint32_t pb = (L::ACC_PAIRS == 2) ? (uint32_t)(j & 1) : 0u;
+        const uint32_t use = (L::ACC_PAIRS == 2) ? (uint32_t)(j >> 1) : (uint32_t)j;    // how often this pair buffer was used before
+        for (int i = 0; i < nch; ++i, ++u) {
+          const int nk = (i == nch - 1) ? nk_last : TC_BK / 8;
+          if (dual) {
+            DT_T(tm3);
+            if (i == 0) {
+              mbar_wait(&tmem_empty[pb * 2 + hmine], (use & 1u) ^ 1u);     // the epilogue drained this accumulator
+              tc_fence_after();
+            }
+            DT_T(tm4);
+            DT_ADD(6, tm3, tm4);
+            DT_TR(u, 6 + 2 * hmine);
+            batch(hmine, pb, i, nk);
+            if (i == nch - 1) umma_commit(&tmem_full[pb * 2 + hmine]);    // a commit tracks all MMAs issued so far by this thread
+            umma_commit(&a_empty[sa]);                                     // both issuers arrive: count 2
+            umma_commit(&b_empty[sb]);
+            DT_T(tm5);
+            DT_ADD(7, tm4, tm5);
+            DT_TR(u, 7 + 2 * hmine);
+            if (u + 1 < total_units) wait_next();
+          } else {
+            DT_T(tm3);
+            if (i == 0) {
+              mbar_wait(&tmem_empty[pb * 2 + 0], (use & 1u) ^ 1u);
+              tc_fence_after();
+            }
+            DT_T(tm4);
+            DT_TR(u, 6);
+            batch(0u, pb, i, nk);
+            if (i == nch - 1) umma_commit(&tmem_full[pb * 2 + 0]);
+            DT_T(tm5);
+            DT_TR(u, 7);
+            if (u + 1 < total_units) wait_next();
+            DT_T(tm6);
+            if (i == 0) {
+              mbar_wait(&tmem_empty[pb * 2 + 1], (use & 1u) ^ 1u);
+              tc_fence_after();
+            }
+            DT_T(tm7);
+            DT_TR(u, 8);
+            batch(1u, pb, i, nk);
+            if (i == nch - 1) umma_commit(&tmem_full[pb * 2 + 1]);
+            umma_commit(&a_empty[sa]);
+            umma_commit(&b_empty[sb]);
+            DT_T(tm8);
+            DT_TR(u, 9);
+            DT_ADD(6, tm3, tm4);
+            DT_ADD(6, tm6, tm7);
+            DT_ADD(7, tm4, tm5);
+            DT_ADD(7, tm7, tm8);
+          }
+          if (++sa == (uint32_t)AS) { sa = 0; pha ^= 1u; }
+          if (++sb == (uint32_t)BS) { sb = 0; phb ^= 1u; }
         }
       }
     }
+    __syncwarp();
   } else if (warp >= 4 && warp < 8) {
     // ===== epilogue warps 4..7: TMEM lane quarter q = warp % 4 =====
     const int q = warp & 3;
@@ -413,7 +467,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
         // (before that group's stores) -- with one accumulator buffer per half tile (N_TILE = 128) the drain is exposed.
         constexpr int NGRP = N_TILE / 32;
         const int ngrp = min(NGRP, (p.Cout - n0 + 31) >> 5);         // warp-uniform, >= 1
-        const bool no_store = (p.flags & 2) != 0;
+        const bool no_store = DT_FLAG(2);
         uint32_t v2[2][32];
         tmem_ld32(tacc, v2[0]);
 #pragma unroll
@@ -498,85 +552,96 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
         if ((warp & 3) == 0) DT_TR(u, 1);
         const float* in_stage = reinterpret_cast<const float*>(smem + s * L::IN_BYTES);
         const float* wd = reinterpret_cast<const float*>(smem + L::OFF_WD) + (size_t)i * CC * L::WD_FLOATS;
-        uint64_t acc[4][2][4];       // [channel i4][half / output row h][pixel] = (depthwise output 2 ci, 2 ci + 1)
-        if (p.flags & 4) {
+        // Two passes of 2 of the thread's 4 channels (i4 = 2 hp, 2 hp + 1): 32 accumulator registers instead of 64, so that
+        // THREE producer groups fit the register file (640 threads x 96) -- the event trace showed the producers, at two
+        // groups, as the pacing stage once the MMA issue loop was slim (stencil ~2200 cycles per unit and group, latency-bound).
+        const uint32_t a_st = a_ring + (uint32_t)(sa * L::AST_COLS) + lane_base;
 #pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4)
+        for (int hp = 0; hp < 2; ++hp) {
+          uint64_t acc[2][2][4];       // [channel i4 - 2 hp][half / output row h][pixel] = (depthwise output 2 ci, 2 ci + 1)
+          if (DT_FLAG(4)) {
+#pragma unroll
+            for (int i2 = 0; i2 < 2; ++i2)
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) acc[i2][h][x] = (uint64_t)(u + x);
+          } else
+#pragma unroll
+          for (int i2 = 0; i2 < 2; ++i2) {
+            const int ci = 4 * (2 * hp + i2) + ph;
+            const ulonglong2* wv = reinterpret_cast<const ulonglong2*>(wd + ci * L::WD_FLOATS);
+            uint64_t w[9], bias;       // w[tap] = (weight of output 2 ci, weight of output 2 ci + 1)
+            {
+              const ulonglong2 t0 = wv[0], t1 = wv[1], t2 = wv[2], t3 = wv[3], t4 = wv[4];
+              w[0] = t0.x; w[1] = t0.y; w[2] = t1.x; w[3] = t1.y; w[4] = t2.x; w[5] = t2.y; w[6] = t3.x; w[7] = t3.y; w[8] = t4.x;
+              bias = t4.y;
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int x = 0; x < 4; ++x) acc[i4][h][x] = (uint64_t)(u + x);
-        } else
+              for (int x = 0; x < 4; ++x) acc[i2][h][x] = bias;
+            const float* src = in_stage + ci * CHS + win_off;
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const int ci = 4 * i4 + ph;
-          const ulonglong2* wv = reinterpret_cast<const ulonglong2*>(wd + ci * L::WD_FLOATS);
-          uint64_t w[9], bias;       // w[tap] = (weight of output 2 ci, weight of output 2 ci + 1)
-          {
-            const ulonglong2 t0 = wv[0], t1 = wv[1], t2 = wv[2], t3 = wv[3], t4 = wv[4];
-            w[0] = t0.x; w[1] = t0.y; w[2] = t1.x; w[3] = t1.y; w[4] = t2.x; w[5] = t2.y; w[6] = t3.x; w[7] = t3.y; w[8] = t4.x;
-            bias = t4.y;
-          }
+            for (int rr = 0; rr < 4; ++rr) {
+              const float4 a = *reinterpret_cast<const float4*>(src + rr * BW);
+              float left = __shfl_up_sync(0xffffffffu, a.w, 4), right = __shfl_down_sync(0xffffffffu, a.x, 4);
+              if (lb | rb) {
+                const float e = src[rr * BW + edge_off];
+                if (lb) left = e; else right = e;
+              }
+              const float v[6] = {left, a.x, a.y, a.z, a.w, right};
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
+              for (int h = 0; h < 2; ++h) {
+                const int dy = rr - h;         // output row h reads input rows h .. h + 2
+                if (dy < 0 || dy > 2) continue;
 #pragma unroll
-            for (int x = 0; x < 4; ++x) acc[i4][h][x] = bias;
-          const float* src = in_stage + ci * CHS + win_off;
+                for (int x = 0; x < 4; ++x)
 #pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const float4 a = *reinterpret_cast<const float4*>(src + rr * BW);
-            float left = __shfl_up_sync(0xffffffffu, a.w, 4), right = __shfl_down_sync(0xffffffffu, a.x, 4);
-            if (lb | rb) {
-              const float e = src[rr * BW + edge_off];
-              if (lb) left = e; else right = e;
-            }
-            const float v[6] = {left, a.x, a.y, a.z, a.w, right};
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int dy = rr - h;         // output row h reads input rows h .. h + 2
-              if (dy < 0 || dy > 2) continue;
-#pragma unroll
-              for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) acc[i4][h][x] = fma2_bcast(w[3 * dy + dx], v[x + dx], acc[i4][h][x]);
-            }
-          }
-        }
-        // the A stage is needed only now: the stencil of this unit overlapped the MMAs still reading the stage
-        if ((warp & 3) == 0) DT_TR(u, 2);
-        mbar_wait(&a_empty[sa], ((u / AS) & 1u) ^ 1u);
-        DT_T(tp2);
-        if ((warp & 3) == 0) DT_TR(u, 3);
-        tc_fence_after();
-        const uint32_t a_st = a_ring + (uint32_t)(sa * L::AST_COLS) + lane_base;
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int g2 = 0; g2 < 2; ++g2) {
-              // 16-lane group g2 of the quarter: TMEM lanes c + 8 (2 g2) and c + 8 (2 g2 + 1) = pixels x = 2 g2, 2 g2 + 1;
-              // K columns 8 i4 + 2 ph + {0, 1}
-              const uint32_t t = a_st + (uint32_t)(h * L::AH_COLS + 8 * i4) + ((uint32_t)(16 * g2) << 16);
-              float o0, o1, o2, o3;
-              unpack2(acc[i4][h][2 * g2], o0, o1);
-              unpack2(acc[i4][h][2 * g2 + 1], o2, o3);
-              if (X3) {
-                const float h0 = tf32_hi(o0), h1 = tf32_hi(o1), h2 = tf32_hi(o2), h3 = tf32_hi(o3);
-                tmem_st_16x256b_x1(t, __float_as_uint(h0), __float_as_uint(h1), __float_as_uint(h2), __float_as_uint(h3));
-                tmem_st_16x256b_x1(t + 32u, __float_as_uint(o0 - h0), __float_as_uint(o1 - h1), __float_as_uint(o2 - h2),
-                                   __float_as_uint(o3 - h3));
-              } else {
-                tmem_st_16x256b_x1(t, __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
+                  for (int dx = 0; dx < 3; ++dx) acc[i2][h][x] = fma2_bcast(w[3 * dy + dx], v[x + dx], acc[i2][h][x]);
               }
             }
+          }
+          if (hp == 0) {
+            // the A stage is needed only now: half the stencil of this unit overlapped the MMAs still reading the stage
+            if ((warp & 3) == 0) DT_TR(u, 2);
+            mbar_wait(&a_empty[sa], ((u / AS) & 1u) ^ 1u);
+            DT_T(tp2a);
+            if (warp == 8) DT_ADD(1, tp1, tp2a);
+            if ((warp & 3) == 0) DT_TR(u, 3);
+            tc_fence_after();
+          } else {
+            mbar_arrive(&in_empty[s]);       // every shared-memory read of the box is done (release): the stage can be refilled
+          }
+#pragma unroll
+          for (int i2 = 0; i2 < 2; ++i2)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int g2 = 0; g2 < 2; ++g2) {
+                // 16-lane group g2 of the quarter: TMEM lanes c + 8 (2 g2) and c + 8 (2 g2 + 1) = pixels x = 2 g2, 2 g2 + 1;
+                // K columns 8 i4 + 2 ph + {0, 1}
+                const uint32_t t = a_st + (uint32_t)(h * L::AH_COLS + 8 * (2 * hp + i2)) + ((uint32_t)(16 * g2) << 16);
+                float o0, o1, o2, o3;
+                unpack2(acc[i2][h][2 * g2], o0, o1);
+                unpack2(acc[i2][h][2 * g2 + 1], o2, o3);
+                if (X3) {
+                  const float h0 = tf32_hi(o0), h1 = tf32_hi(o1), h2 = tf32_hi(o2), h3 = tf32_hi(o3);
+                  tmem_st_16x256b_x1(t, __float_as_uint(h0), __float_as_uint(h1), __float_as_uint(h2), __float_as_uint(h3));
+                  tmem_st_16x256b_x1(t + 32u, __float_as_uint(o0 - h0), __float_as_uint(o1 - h1), __float_as_uint(o2 - h2),
+                                     __float_as_uint(o3 - h3));
+                } else {
+                  tmem_st_16x256b_x1(t, __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
+                }
+              }
+        }
+        DT_T(tp2);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&a_full[sa]);
-        mbar_arrive(&in_empty[s]);
         DT_T(tp3);
         if ((warp & 3) == 0) DT_TR(u, 4);
-        if (warp == 8) { DT_ADD(0, tp0, tp1); DT_ADD(1, tp1, tp2); DT_ADD(2, tp2, tp3); DT_INC(3); }
+        if (warp == 8) { DT_ADD(0, tp0, tp1); DT_ADD(2, tp2, tp3); DT_INC(3); }
       }
     }
   }
@@ -593,6 +658,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
 #undef DT_ADD
 #undef DT_INC
 #undef DT_TR
+#undef DT_FLAG
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
