@@ -137,7 +137,10 @@ struct DtCfg {
   static constexpr int WD_MAX_BYTES = WD_MAXC * WD_FLOATS * 4;   // nchunks * 16 rows of 80 B at the END of the carve-up (run-time size)
   static constexpr int B_BYTES = N_TILE * TC_BK * 4;
   static constexpr int BST_BYTES = (X3 ? 2 : 1) * B_BYTES;
-  static constexpr int NG = BIG ? 2 : 3;                  // producer groups (128 threads each); BIG: no room for a fourth input stage
+  // producer groups (128 threads each).  THREE groups (two-pass stencil with 32 accumulator registers so that 640 threads fit,
+  // a fourth input stage) were built when the event trace showed the producers as the pacing stage: parity-green, but slower
+  // (12 layers 3.64 ms against 3.35 ms) -- more warps fight for the same issue slots, shared-memory port and FP32 pipe.
+  static constexpr int NG = 2;
   // TMEM: accumulators [pair buffer][half] x N_TILE columns, then the A ring (per stage: half 0 hi | lo, half 1 hi | lo)
   static constexpr int ACC_PAIRS = (N_TILE <= 64) ? 2 : 1;
   static constexpr int ACC_COLS = ACC_PAIRS * 2 * N_TILE;
@@ -146,8 +149,8 @@ struct DtCfg {
   static constexpr int AS = ((512 - ACC_COLS) / AST_COLS) > 4 ? 4 : ((512 - ACC_COLS) / AST_COLS);
   static_assert(AS >= 2, "A ring");
   // BIG (more than 256 input channels: 40 KB of depthwise weights, >= 16 chunks per pair) trades ring depth for the table
-  static constexpr int BS = (BIG || N_TILE > 64) ? 2 : 3; // pointwise-weight ring: its TMA loads must cover an L2 round trip
-  static constexpr int IS = BIG ? 3 : (N_TILE <= 64 ? 5 : 4);   // input ring: every producer group holds a stage while it works, + >= 1 in flight
+  static constexpr int BS = BIG ? 2 : 3;                  // pointwise-weight ring: its TMA loads must cover an L2 round trip
+  static constexpr int IS = (N_TILE <= 64 && !BIG) ? 5 : 3;   // input ring (the TMA thread runs far ahead of the producers anyway)
   static_assert(IS >= 2, "input ring");
   static constexpr int OFF_BR = ((IS * IN_BYTES + 1023) / 1024) * 1024;
   static constexpr int OFF_BAR = OFF_BR + BS * BST_BYTES;
@@ -173,8 +176,12 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
   uint64_t* in_full = bars;                       // [IS] input box landed (TMA tx)
   uint64_t* in_empty = in_full + IS;              // [IS] producer group done with the stage (128 arrivals)
   uint64_t* a_full = in_empty + IS;               // [AS] A operand of both halves in TMEM (128 arrivals)
-  uint64_t* a_empty = a_full + AS;                // [AS] MMAs reading the A stage retired (commit)
-  uint64_t* b_full = a_empty + AS;                // [BS]
+  // [AS][NG] MMAs reading the A stage retired (commit) -- one barrier per (stage, producer group that writes the stage NEXT): a
+  // group visits "its" barrier of a stage once per lcm(AS, NG) units and every visit needs exactly one more completion than the
+  // last, so the phase-parity test cannot alias.  With one barrier per stage and NG > AS a group could find the stage two
+  // completions behind (parity equal again), walk through and overwrite operands still being read.
+  uint64_t* a_empty = a_full + AS;
+  uint64_t* b_full = a_empty + AS * L::NG;        // [BS]
   uint64_t* b_empty = b_full + BS;                // [BS]
   uint64_t* tmem_full = b_empty + BS;             // [2][2] per (pair buffer, half): its MMAs retired (the epilogue starts on half 0 while half 1 finishes)
   uint64_t* tmem_empty = tmem_full + 4;           // [2][2] per (pair buffer, half): drained by the epilogue (128 arrivals)
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
     }
     for (int s = 0; s < AS; ++s) {
       mbar_init(&a_full[s], 128);
-      mbar_init(&a_empty[s], (p.flags & 64) ? 1 : 2);
+      for (int g = 0; g < L::NG; ++g) mbar_init(&a_empty[s * L::NG + g], (p.flags & 64) ? 1 : 2);
     }
     for (int s = 0; s < BS; ++s) {
       mbar_init(&b_full[s], 1);
@@ -332,6 +339,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
       const int nk_last = (min(TC_BK, p.K - (nch - 1) * TC_BK) + 7) >> 3;
       const uint64_t bdesc0 = make_b_desc(smem_u32(b_base));          // stage sb: + sb * BST_BYTES / 16 in the address field
       uint32_t u = 0, sa = 0, sb = 0, pha = 0, phb = 0;               // ring positions and phase bits of the CURRENT unit
+      uint32_t gnx = (uint32_t)(AS % L::NG);                          // producer group of unit u + AS: the next writer of stage sa
       // one half-tile batch of unit (sa, sb): 4 k-steps x (hi*hi [+ hi*lo + lo*hi])
       auto batch = [&](uint32_t h, uint32_t pb, int i, int nk) {
         const uint32_t d_tmem = tmem_base + (pb * 2 + h) * N_TILE;
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
             DT_TR(u, 6 + 2 * hmine);
             batch(hmine, pb, i, nk);
             if (i == nch - 1) umma_commit(&tmem_full[pb * 2 + hmine]);    // a commit tracks all MMAs issued so far by this thread
-            umma_commit(&a_empty[sa]);                                     // both issuers arrive: count 2
+            umma_commit(&a_empty[sa * (uint32_t)L::NG + gnx]);            // both issuers arrive: count 2
             umma_commit(&b_empty[sb]);
             DT_T(tm5);
             DT_ADD(7, tm4, tm5);
@@ -419,7 +427,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
             DT_TR(u, 8);
             batch(1u, pb, i, nk);
             if (i == nch - 1) umma_commit(&tmem_full[pb * 2 + 1]);
-            umma_commit(&a_empty[sa]);
+            umma_commit(&a_empty[sa * (uint32_t)L::NG + gnx]);
             umma_commit(&b_empty[sb]);
             DT_T(tm8);
             DT_TR(u, 9);
@@ -430,6 +438,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
           }
           if (++sa == (uint32_t)AS) { sa = 0; pha ^= 1u; }
           if (++sb == (uint32_t)BS) { sb = 0; phb ^= 1u; }
+          if (++gnx == (uint32_t)L::NG) gnx = 0;
         }
       }
     }
@@ -541,7 +550,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
     // RQ q + 2 cy (box rows +0 .. +3), its LDS.128 at box column 4 cx + 4, the edge values at 4 cx + 3 / 4 cx + 8
     const int win_off = (RQ * q + 2 * cy) * BW + 4 * cx + 4;
     const int edge_off = lb ? -1 : 4;
-    uint32_t u = 0;
+    uint32_t u = 0, aph = 0;        // aph: phase bit per A stage of this group's hand-back barriers
     for (int j = 0; j < my_pairs; ++j) {
       for (int i = 0; i < nch; ++i, ++u) {
         if ((int)(u % (uint32_t)L::NG) != g) continue;
@@ -552,96 +561,88 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
         if ((warp & 3) == 0) DT_TR(u, 1);
         const float* in_stage = reinterpret_cast<const float*>(smem + s * L::IN_BYTES);
         const float* wd = reinterpret_cast<const float*>(smem + L::OFF_WD) + (size_t)i * CC * L::WD_FLOATS;
-        // Two passes of 2 of the thread's 4 channels (i4 = 2 hp, 2 hp + 1): 32 accumulator registers instead of 64, so that
-        // THREE producer groups fit the register file (640 threads x 96) -- the event trace showed the producers, at two
-        // groups, as the pacing stage once the MMA issue loop was slim (stencil ~2200 cycles per unit and group, latency-bound).
-        const uint32_t a_st = a_ring + (uint32_t)(sa * L::AST_COLS) + lane_base;
+        uint64_t acc[4][2][4];       // [channel i4][half / output row h][pixel] = (depthwise output 2 ci, 2 ci + 1)
+        if (DT_FLAG(4)) {
 #pragma unroll
-        for (int hp = 0; hp < 2; ++hp) {
-          uint64_t acc[2][2][4];       // [channel i4 - 2 hp][half / output row h][pixel] = (depthwise output 2 ci, 2 ci + 1)
-          if (DT_FLAG(4)) {
-#pragma unroll
-            for (int i2 = 0; i2 < 2; ++i2)
-#pragma unroll
-              for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int x = 0; x < 4; ++x) acc[i2][h][x] = (uint64_t)(u + x);
-          } else
-#pragma unroll
-          for (int i2 = 0; i2 < 2; ++i2) {
-            const int ci = 4 * (2 * hp + i2) + ph;
-            const ulonglong2* wv = reinterpret_cast<const ulonglong2*>(wd + ci * L::WD_FLOATS);
-            uint64_t w[9], bias;       // w[tap] = (weight of output 2 ci, weight of output 2 ci + 1)
-            {
-              const ulonglong2 t0 = wv[0], t1 = wv[1], t2 = wv[2], t3 = wv[3], t4 = wv[4];
-              w[0] = t0.x; w[1] = t0.y; w[2] = t1.x; w[3] = t1.y; w[4] = t2.x; w[5] = t2.y; w[6] = t3.x; w[7] = t3.y; w[8] = t4.x;
-              bias = t4.y;
-            }
+          for (int i4 = 0; i4 < 4; ++i4)
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int x = 0; x < 4; ++x) acc[i2][h][x] = bias;
-            const float* src = in_stage + ci * CHS + win_off;
+              for (int x = 0; x < 4; ++x) acc[i4][h][x] = (uint64_t)(u + x);
+        } else
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-              const float4 a = *reinterpret_cast<const float4*>(src + rr * BW);
-              float left = __shfl_up_sync(0xffffffffu, a.w, 4), right = __shfl_down_sync(0xffffffffu, a.x, 4);
-              if (lb | rb) {
-                const float e = src[rr * BW + edge_off];
-                if (lb) left = e; else right = e;
-              }
-              const float v[6] = {left, a.x, a.y, a.z, a.w, right};
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int ci = 4 * i4 + ph;
+          const ulonglong2* wv = reinterpret_cast<const ulonglong2*>(wd + ci * L::WD_FLOATS);
+          uint64_t w[9], bias;       // w[tap] = (weight of output 2 ci, weight of output 2 ci + 1)
+          {
+            const ulonglong2 t0 = wv[0], t1 = wv[1], t2 = wv[2], t3 = wv[3], t4 = wv[4];
+            w[0] = t0.x; w[1] = t0.y; w[2] = t1.x; w[3] = t1.y; w[4] = t2.x; w[5] = t2.y; w[6] = t3.x; w[7] = t3.y; w[8] = t4.x;
+            bias = t4.y;
+          }
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int dy = rr - h;         // output row h reads input rows h .. h + 2
-                if (dy < 0 || dy > 2) continue;
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
+            for (int x = 0; x < 4; ++x) acc[i4][h][x] = bias;
+          const float* src = in_stage + ci * CHS + win_off;
 #pragma unroll
-                  for (int dx = 0; dx < 3; ++dx) acc[i2][h][x] = fma2_bcast(w[3 * dy + dx], v[x + dx], acc[i2][h][x]);
-              }
+          for (int rr = 0; rr < 4; ++rr) {
+            const float4 a = *reinterpret_cast<const float4*>(src + rr * BW);
+            float left = __shfl_up_sync(0xffffffffu, a.w, 4), right = __shfl_down_sync(0xffffffffu, a.x, 4);
+            if (lb | rb) {
+              const float e = src[rr * BW + edge_off];
+              if (lb) left = e; else right = e;
+            }
+            const float v[6] = {left, a.x, a.y, a.z, a.w, right};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int dy = rr - h;         // output row h reads input rows h .. h + 2
+              if (dy < 0 || dy > 2) continue;
+#pragma unroll
+              for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) acc[i4][h][x] = fma2_bcast(w[3 * dy + dx], v[x + dx], acc[i4][h][x]);
             }
           }
-          if (hp == 0) {
-            // the A stage is needed only now: half the stencil of this unit overlapped the MMAs still reading the stage
-            if ((warp & 3) == 0) DT_TR(u, 2);
-            mbar_wait(&a_empty[sa], ((u / AS) & 1u) ^ 1u);
-            DT_T(tp2a);
-            if (warp == 8) DT_ADD(1, tp1, tp2a);
-            if ((warp & 3) == 0) DT_TR(u, 3);
-            tc_fence_after();
-          } else {
-            mbar_arrive(&in_empty[s]);       // every shared-memory read of the box is done (release): the stage can be refilled
-          }
-#pragma unroll
-          for (int i2 = 0; i2 < 2; ++i2)
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-              for (int g2 = 0; g2 < 2; ++g2) {
-                // 16-lane group g2 of the quarter: TMEM lanes c + 8 (2 g2) and c + 8 (2 g2 + 1) = pixels x = 2 g2, 2 g2 + 1;
-                // K columns 8 i4 + 2 ph + {0, 1}
-                const uint32_t t = a_st + (uint32_t)(h * L::AH_COLS + 8 * (2 * hp + i2)) + ((uint32_t)(16 * g2) << 16);
-                float o0, o1, o2, o3;
-                unpack2(acc[i2][h][2 * g2], o0, o1);
-                unpack2(acc[i2][h][2 * g2 + 1], o2, o3);
-                if (X3) {
-                  const float h0 = tf32_hi(o0), h1 = tf32_hi(o1), h2 = tf32_hi(o2), h3 = tf32_hi(o3);
-                  tmem_st_16x256b_x1(t, __float_as_uint(h0), __float_as_uint(h1), __float_as_uint(h2), __float_as_uint(h3));
-                  tmem_st_16x256b_x1(t + 32u, __float_as_uint(o0 - h0), __float_as_uint(o1 - h1), __float_as_uint(o2 - h2),
-                                     __float_as_uint(o3 - h3));
-                } else {
-                  tmem_st_16x256b_x1(t, __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
-                }
-              }
+        }
+        // the A stage is needed only now: the stencil of this unit overlapped the MMAs still reading the stage
+        if ((warp & 3) == 0) DT_TR(u, 2);
+        if (u >= (uint32_t)AS) {       // the stage had a reader: wait for this group's own hand-back barrier of the stage
+          mbar_wait(&a_empty[sa * L::NG + g], (aph >> sa) & 1u);
+          aph ^= 1u << sa;
         }
         DT_T(tp2);
+        if ((warp & 3) == 0) DT_TR(u, 3);
+        tc_fence_after();
+        const uint32_t a_st = a_ring + (uint32_t)(sa * L::AST_COLS) + lane_base;
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2) {
+              // 16-lane group g2 of the quarter: TMEM lanes c + 8 (2 g2) and c + 8 (2 g2 + 1) = pixels x = 2 g2, 2 g2 + 1;
+              // K columns 8 i4 + 2 ph + {0, 1}
+              const uint32_t t = a_st + (uint32_t)(h * L::AH_COLS + 8 * i4) + ((uint32_t)(16 * g2) << 16);
+              float o0, o1, o2, o3;
+              unpack2(acc[i4][h][2 * g2], o0, o1);
+              unpack2(acc[i4][h][2 * g2 + 1], o2, o3);
+              if (X3) {
+                const float h0 = tf32_hi(o0), h1 = tf32_hi(o1), h2 = tf32_hi(o2), h3 = tf32_hi(o3);
+                tmem_st_16x256b_x1(t, __float_as_uint(h0), __float_as_uint(h1), __float_as_uint(h2), __float_as_uint(h3));
+                tmem_st_16x256b_x1(t + 32u, __float_as_uint(o0 - h0), __float_as_uint(o1 - h1), __float_as_uint(o2 - h2),
+                                   __float_as_uint(o3 - h3));
+              } else {
+                tmem_st_16x256b_x1(t, __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
+              }
+            }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&a_full[sa]);
+        mbar_arrive(&in_empty[s]);
         DT_T(tp3);
         if ((warp & 3) == 0) DT_TR(u, 4);
-        if (warp == 8) { DT_ADD(0, tp0, tp1); DT_ADD(2, tp2, tp3); DT_INC(3); }
+        if (warp == 8) { DT_ADD(0, tp0, tp1); DT_ADD(1, tp1, tp2); DT_ADD(2, tp2, tp3); DT_INC(3); }
       }
     }
   }
