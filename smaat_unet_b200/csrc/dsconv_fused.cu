@@ -64,9 +64,11 @@ struct DsCfg {
   static constexpr int BST_BYTES = (X3 ? 2 : 1) * B_BYTES;     // B ring stage: hi [+ lo]
   static constexpr int OFF_ALO = A_BYTES;
   static constexpr int OFF_BLO = B_BYTES;
-  static constexpr int NG = 3;                                  // depthwise producer groups (128 threads each)
   // A ring: 3 stages in TF32X3 (32 KB each; the input ring must stay deep enough to cover HBM latency), 4 in TF32
   static constexpr int AS = X3 ? ((KPL == 1 && N_TILE > 64) ? 2 : 3) : 4;
+  // depthwise producer groups (128 threads each).  NG <= AS always: the per-stage a_empty barriers are tested by phase parity,
+  // which is only unambiguous while a group can never be two hand-backs of a stage behind (see csrc/dsconv_tmem.cu)
+  static constexpr int NG = AS < 3 ? 2 : 3;
   static constexpr int BS = X3 ? 2 : 4;                         // weight ring, prefetched by its own warp
   static constexpr int IS_FIT = (218 * 1024 - AS * AST_BYTES - BS * BST_BYTES) / IN_BYTES;
   static constexpr int IS = IS_FIT > 8 ? 8 : IS_FIT;           // input ring: as deep as shared memory allows
@@ -74,6 +76,7 @@ struct DsCfg {
   static constexpr int OFF_BR = OFF_A + AS * AST_BYTES;
   static constexpr int OFF_BAR = OFF_BR + BS * BST_BYTES;
   static constexpr int BAR_BYTES = 512;
+  static_assert((IS * NG + IS + 2 * AS + 2 * BS + 4) * 8 + 8 <= BAR_BYTES, "barrier block");
   static constexpr int AFF_N = 128;
   static constexpr int TOTAL = OFF_BAR + BAR_BYTES + 3 * AFF_N * 4 + 1024;   // scale | shift | OutConv weights
   static constexpr uint32_t B_TX = BST_BYTES;
@@ -102,8 +105,11 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
   unsigned char* a_base = smem + L::OFF_A;
   unsigned char* b_base = smem + L::OFF_BR;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* in_full = bars;                       // [IS] TMA input box landed
-  uint64_t* in_empty = in_full + IS;              // [IS] producer group finished reading the box (128 arrivals)
+  // [IS][NG] TMA input box landed, one barrier per (stage, group that reads the fill): a group meets a stage only at every
+  // NG-th of its fills (unless NG divides IS), and TMA loads may complete out of order -- a parity test on a per-stage
+  // barrier could then be satisfied by the wrong fill (csrc/dsconv_tmem.cu has the failure this caused there)
+  uint64_t* in_full = bars;
+  uint64_t* in_empty = in_full + IS * L::NG;      // [IS] producer group finished reading the box (128 arrivals)
   uint64_t* a_full = in_empty + IS;               // [AS] A operand written (128 arrivals)
   uint64_t* a_empty = a_full + AS;                // [AS] MMAs reading the A stage retired (commit)
   uint64_t* b_full = a_empty + AS;                // [BS] weight chunk landed (TMA tx)
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
     tma_prefetch_desc(&map_w);
     if (X3) tma_prefetch_desc(&map_wlo);
     for (int s = 0; s < IS; ++s) {
-      mbar_init(&in_full[s], 1);
+      for (int g = 0; g < L::NG; ++g) mbar_init(&in_full[s * L::NG + g], 1);
       mbar_init(&in_empty[s], 128);
     }
     for (int s = 0; s < AS; ++s) {
@@ -165,14 +171,15 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
         for (int i = 0; i < nch; ++i, ++gc) {
           const int s = gc % IS;
           mbar_wait(&in_empty[s], ((gc / IS) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&in_full[s], L::IN_BYTES);
+          uint64_t* full = &in_full[s * L::NG + (int)(gc % (uint32_t)L::NG)];      // the barrier of the group that reads this chunk
+          mbar_arrive_expect_tx(full, L::IN_BYTES);
           const int cb = i * CC;
           const CUtensorMap* m = (cb < p.C0) ? &map_in0 : &map_in1;
           const int cc = (cb < p.C0) ? cb : cb - p.C0;
           asm volatile(
               "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
                   "r"(smem_u32(smem + s * L::IN_BYTES)),
-              "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(&in_full[s])), "r"(x0 - 4), "r"(y0 - 1), "r"(cc), "r"(b)
+              "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(full)), "r"(x0 - 4), "r"(y0 - 1), "r"(cc), "r"(b)
               : "memory");
           // pull the same chunk of this CTA's NEXT tile into L2 now: by the time it is TMA-loaded the HBM
           // latency is already paid, so a few 15 KB boxes in flight per SM are enough to stream at HBM speed
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
     const int g = (warp - 6) >> 2;
     const int t = threadIdx.x - 192 - 128 * g;  // 0..127
     const int Cin = p.C0 + p.C1;
-    uint32_t gc = 0;
+    uint32_t gc = 0, iph = 0;       // iph: phase bit per input stage of this group's fill barriers
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       for (int i = 0; i < nch; ++i, ++gc) {
         if ((int)(gc % (uint32_t)L::NG) != g) continue;
@@ -405,7 +412,8 @@ __global__ void __launch_bounds__(DsCfg<N_TILE, KPL, PW, X3>::THREADS, 1)
         };
         load_weights(t);
         if (rec) tk0 = clock64();
-        mbar_wait(&in_full[s], (gc / IS) & 1u);
+        mbar_wait(&in_full[s * L::NG + g], (iph >> s) & 1u);
+        iph ^= 1u << s;
         if (rec) tk1 = clock64();
         const int sa = gc % AS;
         mbar_wait(&a_empty[sa], ((gc / AS) & 1u) ^ 1u);  // MMAs that read this A stage 3 chunks ago retired

@@ -155,6 +155,7 @@ struct DtCfg {
   static constexpr int OFF_BR = ((IS * IN_BYTES + 1023) / 1024) * 1024;
   static constexpr int OFF_BAR = OFF_BR + BS * BST_BYTES;
   static constexpr int BAR_BYTES = 512;
+  static_assert((IS * NG + IS + AS + AS * NG + 2 * BS + 8) * 8 + 8 <= BAR_BYTES, "barrier block");
   static constexpr int AFF_N = 512;                        // epilogue affine of ALL output channels (up to 4 passes of 128)
   static constexpr int OFF_WD = OFF_BAR + BAR_BYTES + 3 * AFF_N * 4;
   static constexpr int FIXED = OFF_WD + 1024;             // + alignment slack; + the depthwise-weight table = dynamic shared memory
@@ -173,8 +174,13 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* b_base = smem + L::OFF_BR;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* in_full = bars;                       // [IS] input box landed (TMA tx)
-  uint64_t* in_empty = in_full + IS;              // [IS] producer group done with the stage (128 arrivals)
+  // [IS][NG] input box landed (TMA tx) -- one barrier per (stage, producer group that reads the fill): with IS odd and two groups a
+  // group meets a stage only at every SECOND fill, and a phase-parity test on a per-stage barrier cannot tell "my fill landed"
+  // from "the fill before the other group's landed late" (TMA loads may complete out of order).  The group would read the
+  // wrong box and arrive on in_empty a phase early: over-arrival, an intermittent "unspecified launch failure" (seen on
+  // 576 x 576 inputs in tf32 mode).  Per (stage, group) every visit needs exactly one more completion.
+  uint64_t* in_full = bars;
+  uint64_t* in_empty = in_full + IS * L::NG;      // [IS] producer group done with the stage (128 arrivals)
   uint64_t* a_full = in_empty + IS;               // [AS] A operand of both halves in TMEM (128 arrivals)
   // [AS][NG] MMAs reading the A stage retired (commit) -- one barrier per (stage, producer group that writes the stage NEXT): a
   // group visits "its" barrier of a stage once per lcm(AS, NG) units and every visit needs exactly one more completion than the
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
     tma_prefetch_desc(&map_w);
     if (X3) tma_prefetch_desc(&map_wlo);
     for (int s = 0; s < IS; ++s) {
-      mbar_init(&in_full[s], 1);
+      for (int g = 0; g < L::NG; ++g) mbar_init(&in_full[s * L::NG + g], 1);
       mbar_init(&in_empty[s], 128);
     }
     for (int s = 0; s < AS; ++s) {
@@ -287,14 +293,15 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
           DT_ADD(13, tq0, tq1);
           DT_INC(14);
           DT_TR(u, 0);
-          mbar_arrive_expect_tx(&in_full[s], L::IN_BYTES);
+          uint64_t* full = &in_full[s * L::NG + (int)(u % (uint32_t)L::NG)];      // the barrier of the group that reads unit u
+          mbar_arrive_expect_tx(full, L::IN_BYTES);
           const int cb = i * CC;
           const CUtensorMap* m = (cb < p.C0) ? &map_in0 : &map_in1;
           const int cc = (cb < p.C0) ? cb : cb - p.C0;
           asm volatile(
               "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
                   "r"(smem_u32(smem + s * L::IN_BYTES)),
-              "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(&in_full[s])), "r"(x0 - 4), "r"(y0 - 1), "r"(cc), "r"(b)
+              "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(full)), "r"(x0 - 4), "r"(y0 - 1), "r"(cc), "r"(b)
               : "memory");
           // the same chunk of this CTA's NEXT pair goes to L2 now, so its TMA load later pays L2 latency only
           if (has_next && (p.flags & 1))
@@ -550,13 +557,14 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
     // RQ q + 2 cy (box rows +0 .. +3), its LDS.128 at box column 4 cx + 4, the edge values at 4 cx + 3 / 4 cx + 8
     const int win_off = (RQ * q + 2 * cy) * BW + 4 * cx + 4;
     const int edge_off = lb ? -1 : 4;
-    uint32_t u = 0, aph = 0;        // aph: phase bit per A stage of this group's hand-back barriers
+    uint32_t u = 0, aph = 0, iph = 0;   // phase bit per A stage (hand-back barriers) / per input stage (fill barriers) of THIS group
     for (int j = 0; j < my_pairs; ++j) {
       for (int i = 0; i < nch; ++i, ++u) {
         if ((int)(u % (uint32_t)L::NG) != g) continue;
         const int s = u % IS, sa = u % AS;
         DT_T(tp0);
-        mbar_wait(&in_full[s], (u / IS) & 1u);
+        mbar_wait(&in_full[s * L::NG + g], (iph >> s) & 1u);
+        iph ^= 1u << s;
         DT_T(tp1);
         if ((warp & 3) == 0) DT_TR(u, 1);
         const float* in_stage = reinterpret_cast<const float*>(smem + s * L::IN_BYTES);

@@ -300,6 +300,25 @@ def test_dsconv_ineligible_shapes_fall_back():
         assert_close(m(dev(x)), ref, PW_TOL["tf32x3"], "unfused fallback")
 
 
+def test_dsconv_with_batch_statistics_only_where_a_kernel_has_them():
+    """smaat_dsconv_eligible2(with_stats): the TMEM-operand kernel has no batch-statistics epilogue, so a request with `stats`
+    is either taken by the shared-memory-operand kernel (Cout <= 128) or declined (Cout = 256) -- never an error -- and
+    DepthwiseSeparableConv.run(stats=...) gives the same result and the same sums either way."""
+    for cout, fused in ((64, True), (256, False)):
+        m = S.DepthwiseSeparableConv(16, cout, 3, padding=1, kernels_per_layer=2).cuda().eval()
+        x = dev(rnd(2, 16, 32, 32))
+        assert m.fused_takes(x) is True                      # without statistics both shapes are fused (Cout 256: passes of 128)
+        assert m.fused_takes(x, stats=True) is fused
+        with torch.no_grad():
+            st = ops.new_stats(cout, x.device)
+            z = m.run(x, stats=st)
+            ref = m(x)
+        assert_close(z, ref.double().cpu().numpy(), 1e-5, f"run(stats) Cout={cout}")
+        zs = z.double()
+        sums = torch.stack([zs.sum(dim=(0, 2, 3)), (zs * zs).sum(dim=(0, 2, 3))]).reshape(-1)
+        assert_close(st, sums.cpu().numpy(), 1e-5, f"batch statistics Cout={cout}")
+
+
 @pytest.mark.parametrize("shape", [(2, 3, 8, 12), (1, 5, 64, 64), (2, 2, 288, 288), (3, 4, 18, 20)])
 def test_cbam_pool_with_fused_maxpool(shape):
     """smaat_cbam_pool_maxpool_fwd: global avg/max pools and MaxPool2d(2) from one read (layers.py:107-108, parts_ds.py:48)."""
