@@ -274,8 +274,8 @@ __global__ void __launch_bounds__(DtCfg<N_TILE, PW, X3, BIG>::THREADS, 1)
 
   if (warp == 0) {
     // ===== TMA: one input halo box per unit =====
-    // [lane test, not elect.sync: with elect.sync here (and in the weight loader) the many-chunk concat case of
-    // tests/test_gpu_kernels.py produced wrong results; these loops issue 1-3 instructions per unit, nothing to gain]
+    // [plain lane test: these loops issue 1-3 instructions per unit, the single-thread elect.sync region of the MMA issuers
+    // has nothing to gain here]
     if (lane == 0) {
       uint32_t u = 0;
       for (int j = 0; j < my_pairs; ++j) {
