@@ -343,7 +343,10 @@ class ChannelAttention(nn.Module):
         """sigmoid(MLP(avg) + MLP(max)) as a (B, C) tensor.  ``with_maxpool``: also return MaxPool2d(2)(x) (or None), computed
         in the same read of x as the global pools."""
         l1, l2 = self.MLP[1], self.MLP[3]
-        one = ops.cbam_pool_mlp(x, l1.weight.detach(), l1.bias.detach(), l2.weight.detach(), l2.bias.detach(), with_maxpool=with_maxpool)
+        # 512 channels: the MLP run by the last-arriving pooling CTA of each image measured SLOWER than a second launch
+        # (tools/time_cbam_pool.py, B = 32: 57.6 vs 24.5 us at 18 x 18, 49.8 vs 37.7 us at 36 x 36; equal from 72 x 72 up)
+        one = None if x.shape[1] >= 512 else ops.cbam_pool_mlp(x, l1.weight.detach(), l1.bias.detach(), l2.weight.detach(), l2.bias.detach(),
+                                                               with_maxpool=with_maxpool)
         if one is not None:          # pools + MLP + sigmoid (+ the 2x2 max-pool) in one launch
             sc, _, _, pooled = one
             return (sc, pooled) if with_maxpool else sc

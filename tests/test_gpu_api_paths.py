@@ -152,7 +152,7 @@ def test_reference_call_order_matches_reference_golden(name, n_cbams, mode):
     H, W = c["x"][2], c["x"][3]
     if n_cbams >= 4 and H % 16 == 0 and W % 32 == 0:
         # the plain calls reach the pool+max-pool fusion: no standalone max-pool launch is left
-        assert names.count("smaat_maxpool2_fwd") == 0 and names.count("smaat_cbam_pool_mlp_fwd") >= 4, names
+        assert names.count("smaat_maxpool2_fwd") == 0 and names.count("smaat_cbam_pool_mlp_fwd") >= 3, names
     if n_cbams == 0:
         assert names.count("smaat_maxpool2_fwd") == 4
 
@@ -170,7 +170,8 @@ def test_model_forward_is_the_reference_order_and_serving_forward_agrees():
     n2 = [r[0].split("[")[0] for r in p2.records]
     assert_close(y_plain, ref, NET_TOL["tf32x3"], "plain forward")
     assert_close(y_serv, ref, NET_TOL["tf32x3"], "serving forward")
-    assert "smaat_maxpool2_fwd" not in n1 and n1.count("smaat_cbam_pool_mlp_fwd") == 5 and n1.count("smaat_cbam_gate_scale_fwd") == 4   # cbam5 is 18 x 18: W % 4 != 0 -> gate + scale kernels
+    assert "smaat_maxpool2_fwd" not in n1 and n1.count("smaat_cbam_pool_mlp_fwd") == 3 and n1.count("smaat_cbam_gate_scale_fwd") == 4   # cbam5 is 18 x 18: W % 4 != 0 -> gate + scale kernels
+    assert n1.count("smaat_cbam_mlp_fwd") == 2 and n1.count("smaat_cbam_pool_maxpool_fwd") == 1    # the two 512-channel CBAMs: pool and MLP as two launches (faster)
     assert "smaat_outconv_fwd" in n1 and "smaat_outconv_fwd" not in n2 and "smaat_dsconv_outconv_fwd" in n2
 
 
