@@ -443,7 +443,7 @@ def main():
 
     # ---------------- everything below is explanatory; the headline (value, e2e) is in hand.  A watchdog prints the line with what
     # has been measured so far if a later leg stalls (a reported-only leg must never cost the run its number) ----------------
-    via_api = alt = gpu_eager = roof = roof_dw = cpu = train = None
+    via_api = alt = gpu_eager = roof = roof_dw = roof_cbam = cpu = train = None
     kernels = {}
     e2e_meta = (sess.h2d_bytes_per_step, sess.d2h_bytes_per_step, sess.graph is not None)
     emitted = threading.Event()
@@ -457,7 +457,7 @@ def main():
                        "global_batch": B_PER_GPU * world, "pointwise": args.mode, "cuda_graph": e2e_meta[2],
                        "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": "inputs alternate between 2 buffers; a step streams ~40 GB of activations (>> 126 MB L2)"},
-            "roofline": roof, "depthwise_roofline": roof_dw, "kernels": kernels, "cpu_baseline": cpu,
+            "roofline": roof, "depthwise_roofline": roof_dw, "cbam_roofline": roof_cbam, "kernels": kernels, "cpu_baseline": cpu,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": e2e_meta[0],
                     "d2h_bytes_per_step": e2e_meta[1], "ms_per_step": 1e3 * e2e_s / args.steps, "checksum": chk,
                     "checksum_expected": chk_expect},
@@ -555,6 +555,19 @@ def main():
                 "algorithmic_bytes_per_step": d["algorithmic_GB_per_step"] * 1e9, "ms_per_step": d["ms_per_step"],
                 "note": "frac_tensor counts ISSUED tf32 flops (3 MMA passes per product in tf32x3) against half the measured bf16 "
                         "cuBLAS peak; frac_hbm counts algorithmic bytes (input + output of the fused conv) against the measured copy bandwidth"}
+        # CBAM at the level of the op: all cbam_* launches of a forward against 3 |x| (the algorithmic minimum: the global
+        # pools force a second read of x, plus one write) and against the 4 |x| the three-pass design moves
+        ck = [k for k in kernels if k.startswith("smaat_cbam_")]
+        if ck:
+            t_c = sum(kernels[k]["ms_per_step"] for k in ck) * 1e-3
+            x_bytes = 4.0 * B_PER_GPU * sum(c * (SIZE // d) ** 2 for c, d in ((64, 1), (128, 2), (256, 4), (512, 8), (512, 16)))
+            roof_cbam = {"op": "CBAM x5 = ChannelAttention + SpatialAttention (models/layers.py:90-141), all smaat_cbam_* launches",
+                         "launches_per_step": sum(kernels[k]["launches_per_step"] for k in ck), "ms_per_step": t_c * 1e3,
+                         "x_bytes": x_bytes, "bound": "hbm", "peak": hbm, "unit": "GB/s", "peak_source": src,
+                         "achieved_vs_3x_minimum": 3 * x_bytes / t_c / 1e9, "frac_vs_3x_minimum": 3 * x_bytes / t_c / 1e9 / hbm,
+                         "achieved_4x_moved": 4 * x_bytes / t_c / 1e9, "frac_4x_moved": 4 * x_bytes / t_c / 1e9 / hbm,
+                         "note": "per-kernel fractions (each kernel's own algorithmic bytes) are in `kernels`; the max-pool bytes written by "
+                                 "the pool pass for DownDS are not counted here"}
         # the metric's named kernel -- "depthwise % HBM roofline": the standalone depthwise kernel over ALL 18 layers
         # (fusion switched off for this measurement pass only)
         S.set_fused_dsconv(False)
