@@ -28,11 +28,14 @@
 //
 // Warps (512 threads, 1 CTA per SM, persistent over tile pairs):
 //   0        TMA: input halo boxes (PW + 8) x (PHP + 3) x 16 channels, OOB zero fill = padding 1; virtual concat [x0, x1]
-//   1        MMA issuer (one elected lane): per unit 2 halves x 4 k-steps x {A_hi B_hi, A_hi B_lo, A_lo B_hi}; TMEM alloc
+//   1, 3     MMA issuers: one thread each (a single-thread elect.sync region), warp 1 the MMAs of half tile 0, warp 3 those of
+//            half tile 1: per unit and half 4 k-steps x {A_hi B_hi, A_hi B_lo, A_lo B_hi}; warp 1 also allocates TMEM
 //   2        pointwise-weight ring loader (TMA, K-major SW128, hi | lo)
-//   3        (idle; the layer's depthwise weights are staged once, by all threads, before the roles split)
+//            (the layer's depthwise weights are staged once, by all threads, before the roles split)
 //   4..7     epilogue: tcgen05.ld (lane = pixel, 32 columns per step) -> BN affine + ReLU -> NCHW stores (or OutConv dot)
 //   8..15    two depthwise producer groups (group g takes every second unit)
+// Barriers are tested by phase parity, which is only unambiguous while a waiter can never be two completions behind: the rings
+// that are shared between the two producer groups (input fills, A-stage hand-backs) therefore have one barrier per (stage, group).
 #include <stdlib.h>
 
 #include "tc_common.cuh"
